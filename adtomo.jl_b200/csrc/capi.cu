@@ -1,0 +1,698 @@
+// capi.cu -- the C ABI of libadtomo_b200.so (declared in include/adtomo_b200.h).
+// Host-side orchestration only: argument checks, workspace, staging copies, kernel launches.
+// There is deliberately no CPU implementation of any solver in this library.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/adtomo_b200.h"
+#include "kernels_v0.cuh"
+
+using namespace adtomo;
+
+static thread_local std::string g_err = "";
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ADTOMO_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+struct adtomo_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    long long launches = 0;
+    std::map<std::string, std::pair<void *, size_t>> ws;
+    std::mutex mu;
+    // per-phase device timing of the last call: pairs of events around the kernels of each phase
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<std::pair<int, int>> ev_used;   // (phase, pool index)
+};
+
+enum { PH_FWD = 0, PH_MISFIT = 1, PH_ADJ_SETUP = 2, PH_ADJ_SWEEP = 3, PH_ADJ_FINISH = 4, PH_COUNT = 5 };
+
+static void phase_reset(adtomo_ctx *c) { c->ev_used.clear(); }
+static int phase_begin(adtomo_ctx *c, int phase) {
+    size_t k = c->ev_used.size();
+    if (k >= c->ev_pool.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
+        c->ev_pool.push_back({a, b});
+    }
+    c->ev_used.push_back({phase, (int)k});
+    cudaEventRecord(c->ev_pool[k].first, c->stream);
+    return (int)k;
+}
+static void phase_end(adtomo_ctx *c, int k) {
+    if (k >= 0) cudaEventRecord(c->ev_pool[k].second, c->stream);
+}
+
+// grow-only named device buffers
+static int ws_get(adtomo_ctx *c, const char *name, size_t bytes, void **out) {
+    auto &slot = c->ws[name];
+    if (slot.second < bytes) {
+        if (slot.first) {
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaFree(slot.first));
+            slot.first = nullptr;
+            slot.second = 0;
+        }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&slot.first, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            CK(cudaMalloc(&slot.first, want));
+        }
+        slot.second = want;
+    }
+    *out = slot.first;
+    return 0;
+}
+#define WS(ctx, name, type, count, ptr)                                              \
+    do {                                                                             \
+        void *p__;                                                                   \
+        int rc__ = ws_get(ctx, name, sizeof(type) * (size_t)(count), &p__);          \
+        if (rc__) return rc__;                                                       \
+        ptr = (type *)p__;                                                           \
+    } while (0)
+
+extern "C" const char *adtomo_last_error(void) { return g_err.c_str(); }
+extern "C" int adtomo_version(void) { return 100; }
+
+extern "C" int adtomo_create(adtomo_ctx **out, int device) {
+    if (!out) return fail(ADTOMO_ERR_ARG, "adtomo_create: null out pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ADTOMO_ERR_CUDA, "adtomo_create: no CUDA device (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= ndev) return fail(ADTOMO_ERR_ARG, "adtomo_create: device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    adtomo_ctx *c = new adtomo_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+
+extern "C" int adtomo_destroy(adtomo_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->ws)
+        if (kv.second.first) cudaFree(kv.second.first);
+    for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int adtomo_synchronize(adtomo_ctx *c) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" unsigned long long adtomo_stream(adtomo_ctx *c) { return c ? (unsigned long long)(uintptr_t)c->stream : 0ULL; }
+extern "C" long long adtomo_launch_count(adtomo_ctx *c) { return c ? c->launches : 0; }
+extern "C" double adtomo_last_kernel_ms(adtomo_ctx *c) {
+    if (!c || !c->timed) return -1.0;
+    cudaSetDevice(c->device);
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+extern "C" double adtomo_last_phase_ms(adtomo_ctx *c, int phase) {
+    if (!c) return -1.0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    double tot = 0.0;
+    for (auto &u : c->ev_used) {
+        if (u.first != phase) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[u.second].first, c->ev_pool[u.second].second) == cudaSuccess) tot += ms;
+        else cudaGetLastError();
+    }
+    return tot;
+}
+
+static adtomo_ctx *default_ctx(int *rc) {
+    static thread_local adtomo_ctx *c = nullptr;
+    *rc = 0;
+    if (!c) *rc = adtomo_create(&c, -1);
+    return c;
+}
+
+static int check_launch(adtomo_ctx *c, const char *what) {
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ADTOMO_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+#define LAUNCHED(c, what)                     \
+    do {                                      \
+        int rc__ = check_launch(c, what);     \
+        if (rc__) return rc__;                \
+    } while (0)
+
+// device pointer for an input: either the caller's (DEVICE) or a staged copy (HOST)
+template <typename T>
+static int stage_in(adtomo_ctx *c, const char *name, const T *src, size_t count, int loc, const T **out) {
+    if (loc == ADTOMO_DEVICE) { *out = src; return 0; }
+    T *d;
+    WS(c, name, T, count, d);
+    CK(cudaMemcpyAsync(d, src, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream));
+    *out = d;
+    return 0;
+}
+
+static int elem_grid(adtomo_ctx *c, long long n, int nt = 256) {
+    long long b = (n + nt - 1) / nt;
+    long long cap = (long long)c->num_sms * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+static size_t free_bytes() {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return (size_t)8 << 30; }
+    return fr;
+}
+
+// ---------------------------------------------------------------------------------------
+// 3D forward on device-resident data (U holds u0 on entry)
+// ---------------------------------------------------------------------------------------
+static constexpr int NT3 = 512;
+
+static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3 &d, double h, double tol,
+                        int max_rounds, int S, int *d_rounds, double *d_errs) {
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fwd3d_v0<NT3>, NT3, 0));
+    if (occ < 1) occ = 1;
+    int grid = std::min(S, c->num_sms * occ);
+    double *scratch;
+    WS(c, "fwd_scratch", double, (size_t)grid * d.N, scratch);
+    int pk = phase_begin(c, PH_FWD);
+    k_fwd3d_v0<NT3><<<grid, NT3, 0, c->stream>>>(dU, scratch, df, d, h, tol, max_rounds, S, d_rounds, d_errs);
+    phase_end(c, pk);
+    LAUNCHED(c, "k_fwd3d_v0");
+    return 0;
+}
+
+static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, const double *dG, const double *df,
+                        double *dGU0, double *dGF, double *dGFsum, const Dims3 &d, double h, int S,
+                        int *d_status) {
+    double *X;
+    unsigned char *code;
+    int *rem;
+    WS(c, "adj_x", double, (size_t)S * d.N, X);
+    WS(c, "adj_code", unsigned char, (size_t)S * d.N, code);
+    WS(c, "adj_rem", int, S, rem);
+    CK(cudaMemsetAsync(rem, 0, sizeof(int) * S, c->stream));
+    int pk = phase_begin(c, PH_ADJ_SETUP);
+    k_adj3d_setup<<<elem_grid(c, d.N * S), 256, 0, c->stream>>>(dU, dU0, dG, X, dGU0, code, rem, d, S);
+    phase_end(c, pk);
+    LAUNCHED(c, "k_adj3d_setup");
+    if (dGF || dGFsum) {
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_v0<NT3>, NT3, 0));
+        if (occ < 1) occ = 1;
+        int grid = std::min(S, c->num_sms * occ);
+        pk = phase_begin(c, PH_ADJ_SWEEP);
+        k_adj3d_v0<NT3><<<grid, NT3, 0, c->stream>>>(dU, dG, X, code, rem, d, S, 4096, d_status);
+        phase_end(c, pk);
+        LAUNCHED(c, "k_adj3d_v0");
+        pk = phase_begin(c, PH_ADJ_FINISH);
+        k_adj3d_finish<<<elem_grid(c, d.N), 256, 0, c->stream>>>(X, df, dGF, dGFsum, d.N, S, h);
+        phase_end(c, pk);
+        LAUNCHED(c, "k_adj3d_finish");
+    }
+    return 0;
+}
+
+static int check_dims3(int m, int n, int l, int S) {
+    if (m < 2 || n < 2 || l < 2) return fail(ADTOMO_ERR_ARG, "3D grid needs m,n,l >= 2 (got %d,%d,%d)", m, n, l);
+    if ((long long)m * n * l >= (1LL << 31)) return fail(ADTOMO_ERR_ARG, "m*n*l must be < 2^31");
+    if (S < 1) return fail(ADTOMO_ERR_ARG, "S must be >= 1 (got %d)", S);
+    return 0;
+}
+
+static int rounds_status(const std::vector<int> &r, int *rounds_out) {
+    int st = 0;
+    for (size_t s = 0; s < r.size(); s++) {
+        if (r[s] < 0) st = ADTOMO_NOT_CONVERGED;
+        if (rounds_out) rounds_out[s] = r[s] < 0 ? -r[s] : r[s];
+    }
+    return st;
+}
+
+extern "C" int adtomo_eikonal3d_forward_batch(adtomo_ctx *c, double *u, const double *u0, const double *f,
+                                              double h, int m, int n, int l, double tol, int max_rounds, int S,
+                                              int *rounds, int loc) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "null context");
+    if (!u || !u0 || !f) return fail(ADTOMO_ERR_ARG, "null field pointer");
+    int rc = check_dims3(m, n, l, S);
+    if (rc) return rc;
+    if (max_rounds <= 0) max_rounds = 20;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    Dims3 d{m, n, l, (long long)m * n * l};
+    const double *df;
+    if ((rc = stage_in(c, "f", f, (size_t)d.N, loc, &df))) return rc;
+    // chunk the sources so that host-staged batches fit the device
+    int Sc = S;
+    if (loc == ADTOMO_HOST) {
+        size_t per = sizeof(double) * (size_t)d.N * 2;
+        size_t budget = free_bytes() / 2;
+        Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
+    }
+    int *d_rounds;
+    WS(c, "rounds", int, S, d_rounds);
+    std::vector<int> hr(S);
+    phase_reset(c);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int s0 = 0; s0 < S; s0 += Sc) {
+        int sc = std::min(Sc, S - s0);
+        double *dU;
+        if (loc == ADTOMO_DEVICE) {
+            dU = u + (size_t)s0 * d.N;
+            if (u != u0)
+                CK(cudaMemcpyAsync(dU, u0 + (size_t)s0 * d.N, sizeof(double) * d.N * sc, cudaMemcpyDeviceToDevice, c->stream));
+        } else {
+            WS(c, "U", double, (size_t)sc * d.N, dU);
+            CK(cudaMemcpyAsync(dU, u0 + (size_t)s0 * d.N, sizeof(double) * d.N * sc, cudaMemcpyHostToDevice, c->stream));
+        }
+        if ((rc = fwd3d_device(c, dU, df, d, h, tol, max_rounds, sc, d_rounds + s0, nullptr))) return rc;
+        if (loc == ADTOMO_HOST)
+            CK(cudaMemcpyAsync(u + (size_t)s0 * d.N, dU, sizeof(double) * d.N * sc, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    CK(cudaMemcpyAsync(hr.data(), d_rounds, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return rounds_status(hr, rounds);
+}
+
+extern "C" int adtomo_eikonal3d_forward(double *u, const double *u0, const double *f, double h, int m, int n, int l,
+                                        double tol, int verbose) {
+    int rc;
+    adtomo_ctx *c = default_ctx(&rc);
+    if (rc) return rc;
+    if (!u || !u0 || !f) return fail(ADTOMO_ERR_ARG, "null field pointer");
+    if ((rc = check_dims3(m, n, l, 1))) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    Dims3 d{m, n, l, (long long)m * n * l};
+    const int max_rounds = 20;   // Eikonal3D.cpp:74
+    double *dU, *dF, *dErr;
+    int *dR;
+    WS(c, "U", double, d.N, dU);
+    WS(c, "f", double, d.N, dF);
+    WS(c, "errs", double, max_rounds, dErr);
+    WS(c, "rounds", int, 1, dR);
+    phase_reset(c);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemcpyAsync(dU, u0, sizeof(double) * d.N, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dF, f, sizeof(double) * d.N, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = fwd3d_device(c, dU, dF, d, h, tol, max_rounds, 1, dR, dErr))) return rc;
+    CK(cudaMemcpyAsync(u, dU, sizeof(double) * d.N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    int hr = 0;
+    double herr[20];
+    CK(cudaMemcpyAsync(&hr, dR, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(herr, dErr, sizeof(double) * max_rounds, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    int nr = hr < 0 ? -hr : hr;
+    if (verbose)
+        for (int i = 0; i < nr; i++) printf("Iteration %d, Error = %0.6e\n", i, herr[i]);   // Eikonal3D.cpp:82-84
+    return hr < 0 ? ADTOMO_NOT_CONVERGED : 0;
+}
+
+extern "C" int adtomo_eikonal3d_backward_batch(adtomo_ctx *c, double *grad_u0, double *grad_f, double *grad_f_sum,
+                                               const double *grad_u, const double *u, const double *u0,
+                                               const double *f, double h, int m, int n, int l, int S, int loc) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "null context");
+    if (!grad_u || !u || !u0 || !f) return fail(ADTOMO_ERR_ARG, "null field pointer");
+    int rc = check_dims3(m, n, l, S);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    Dims3 d{m, n, l, (long long)m * n * l};
+    const double *df;
+    if ((rc = stage_in(c, "f", f, (size_t)d.N, loc, &df))) return rc;
+    int Sc = S;
+    {
+        size_t per = sizeof(double) * (size_t)d.N * (loc == ADTOMO_HOST ? 6 : 1) + (size_t)d.N;
+        size_t budget = free_bytes() / 2;
+        Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
+    }
+    int *d_status;
+    WS(c, "status", int, S, d_status);
+    CK(cudaMemsetAsync(d_status, 0, sizeof(int) * S, c->stream));
+    double *dSum = nullptr, *dSumChunk = nullptr;
+    if (grad_f_sum) {
+        if (loc == ADTOMO_DEVICE) dSum = grad_f_sum;
+        else WS(c, "gfsum", double, d.N, dSum);
+        if (Sc < S) {
+            WS(c, "gfsum_chunk", double, d.N, dSumChunk);
+            CK(cudaMemsetAsync(dSum, 0, sizeof(double) * d.N, c->stream));
+        }
+    }
+    phase_reset(c);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int s0 = 0; s0 < S; s0 += Sc) {
+        int sc = std::min(Sc, S - s0);
+        size_t o = (size_t)s0 * d.N, cnt = (size_t)sc * d.N;
+        const double *dU, *dU0, *dG;
+        double *dGU0 = nullptr, *dGF = nullptr;
+        if (loc == ADTOMO_DEVICE) {
+            dU = u + o; dU0 = u0 + o; dG = grad_u + o;
+            if (grad_u0) dGU0 = grad_u0 + o;
+            if (grad_f) dGF = grad_f + o;
+        } else {
+            double *a, *b, *g;
+            WS(c, "U", double, cnt, a);
+            WS(c, "U0", double, cnt, b);
+            WS(c, "G", double, cnt, g);
+            CK(cudaMemcpyAsync(a, u + o, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(b, u0 + o, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(g, grad_u + o, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->stream));
+            dU = a; dU0 = b; dG = g;
+            if (grad_u0) WS(c, "GU0", double, cnt, dGU0);
+            if (grad_f) WS(c, "GF", double, cnt, dGF);
+        }
+        double *sumTarget = grad_f_sum ? (Sc < S ? dSumChunk : dSum) : nullptr;
+        if ((rc = adj3d_device(c, dU, dU0, dG, df, dGU0, dGF, sumTarget, d, h, sc, d_status + s0))) return rc;
+        if (grad_f_sum && Sc < S) {
+            k_axpy<<<elem_grid(c, d.N), 256, 0, c->stream>>>(dSum, dSumChunk, d.N);
+            LAUNCHED(c, "axpy");
+        }
+        if (loc == ADTOMO_HOST) {
+            if (grad_u0) CK(cudaMemcpyAsync(grad_u0 + o, dGU0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->stream));
+            if (grad_f) CK(cudaMemcpyAsync(grad_f + o, dGF, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    if (grad_f_sum && loc == ADTOMO_HOST)
+        CK(cudaMemcpyAsync(grad_f_sum, dSum, sizeof(double) * d.N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    std::vector<int> hs(S, 1);
+    if (grad_f || grad_f_sum) CK(cudaMemcpyAsync(hs.data(), d_status, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < S; s++)
+        if (hs[s] < 0) return ADTOMO_ADJOINT_FLAGGED;
+    return 0;
+}
+
+extern "C" int adtomo_eikonal3d_backward(double *grad_u0, double *grad_f, const double *grad_u, const double *u,
+                                         const double *u0, const double *f, double h, int m, int n, int l) {
+    int rc;
+    adtomo_ctx *c = default_ctx(&rc);
+    if (rc) return rc;
+    return adtomo_eikonal3d_backward_batch(c, grad_u0, grad_f, nullptr, grad_u, u, u0, f, h, m, n, l, 1, ADTOMO_HOST);
+}
+
+// ---------------------------------------------------------------------------------------
+// 2D
+// ---------------------------------------------------------------------------------------
+static constexpr int NT2 = 128;
+static constexpr size_t SMEM2_MAX = 200 * 1024;
+
+static int check_dims2(int m, int n, int S, const int *ix, const int *jx) {
+    if (m < 1 || n < 1) return fail(ADTOMO_ERR_ARG, "2D grid needs m,n >= 1 cells (got %d,%d)", m, n);
+    if ((long long)(m + 1) * (n + 1) >= (1LL << 31)) return fail(ADTOMO_ERR_ARG, "(m+1)*(n+1) must be < 2^31");
+    if (S < 1) return fail(ADTOMO_ERR_ARG, "S must be >= 1");
+    if (!ix || !jx) return fail(ADTOMO_ERR_ARG, "null source index pointer");
+    for (int s = 0; s < S; s++)
+        if (ix[s] < 0 || ix[s] > m || jx[s] < 0 || jx[s] > n)
+            return fail(ADTOMO_ERR_ARG, "source %d at (%d,%d) outside the %dx%d-node grid", s, ix[s], jx[s], m + 1, n + 1);
+    return 0;
+}
+
+extern "C" int adtomo_eikonal2d_forward_batch(adtomo_ctx *c, double *u, const double *f, int m, int n, double h,
+                                              const int *ix, const int *jx, int S, int *rounds, int loc) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "null context");
+    if (!u || !f) return fail(ADTOMO_ERR_ARG, "null field pointer");
+    int rc = check_dims2(m, n, S, ix, jx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const long long N2 = (long long)(m + 1) * (n + 1);
+    const double *df;
+    if ((rc = stage_in(c, "f", f, (size_t)N2, loc, &df))) return rc;
+    int *dIX, *dJX, *dR;
+    WS(c, "ix", int, S, dIX);
+    WS(c, "jx", int, S, dJX);
+    WS(c, "rounds", int, S, dR);
+    CK(cudaMemcpyAsync(dIX, ix, sizeof(int) * S, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dJX, jx, sizeof(int) * S, cudaMemcpyHostToDevice, c->stream));
+    double *dU = u;
+    if (loc == ADTOMO_HOST) WS(c, "U", double, (size_t)S * N2, dU);
+    const size_t smem = sizeof(double) * 2 * N2;
+    const int use_smem = smem <= SMEM2_MAX;
+    int grid = std::min(S, c->num_sms * (use_smem ? std::max<int>(1, (int)(SMEM2_MAX / std::max<size_t>(smem, 1))) : 2));
+    grid = std::min(grid, c->num_sms * 8);
+    double *gwork = nullptr;
+    if (!use_smem) WS(c, "work2d", double, (size_t)grid * 2 * N2, gwork);
+    if (use_smem) CK(cudaFuncSetAttribute(k_fwd2d<NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_MAX));
+    phase_reset(c);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_fwd2d<NT2><<<grid, NT2, use_smem ? smem : 0, c->stream>>>(dU, df, m, n, h, dIX, dJX, S, dR, gwork, use_smem);
+    LAUNCHED(c, "k_fwd2d");
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    if (loc == ADTOMO_HOST) CK(cudaMemcpyAsync(u, dU, sizeof(double) * S * N2, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int> hr(S);
+    CK(cudaMemcpyAsync(hr.data(), dR, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    int st = rounds_status(hr, rounds);
+    if (st) printf("ERROR: Eikonal does not converge!\n");   // Eikonal.h:88-90
+    return st;
+}
+
+extern "C" int adtomo_eikonal2d_forward(double *u, const double *f, int m, int n, double h, int ix, int jx) {
+    int rc;
+    adtomo_ctx *c = default_ctx(&rc);
+    if (rc) return rc;
+    return adtomo_eikonal2d_forward_batch(c, u, f, m, n, h, &ix, &jx, 1, nullptr, ADTOMO_HOST);
+}
+
+extern "C" int adtomo_eikonal2d_backward_batch(adtomo_ctx *c, double *grad_f, double *grad_f_sum,
+                                               const double *grad_u, const double *u, const double *f, int m, int n,
+                                               double h, const int *ix, const int *jx, int S, int loc) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "null context");
+    if (!grad_u || !u || !f) return fail(ADTOMO_ERR_ARG, "null field pointer");
+    if (!grad_f && !grad_f_sum) return fail(ADTOMO_ERR_ARG, "no output requested");
+    int rc = check_dims2(m, n, S, ix, jx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const long long N2 = (long long)(m + 1) * (n + 1);
+    const double *df, *dU, *dG;
+    if ((rc = stage_in(c, "f", f, (size_t)N2, loc, &df))) return rc;
+    if ((rc = stage_in(c, "U", u, (size_t)S * N2, loc, &dU))) return rc;
+    if ((rc = stage_in(c, "G", grad_u, (size_t)S * N2, loc, &dG))) return rc;
+    int *dIX, *dJX, *dSt;
+    WS(c, "ix", int, S, dIX);
+    WS(c, "jx", int, S, dJX);
+    WS(c, "status", int, S, dSt);
+    CK(cudaMemcpyAsync(dIX, ix, sizeof(int) * S, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dJX, jx, sizeof(int) * S, cudaMemcpyHostToDevice, c->stream));
+    double *dGF;
+    if (loc == ADTOMO_DEVICE && grad_f) dGF = grad_f;
+    else WS(c, "GF", double, (size_t)S * N2, dGF);
+    const long long per = N2 + (N2 + 7) / 8;
+    const size_t smem = sizeof(double) * per;
+    const int use_smem = smem <= SMEM2_MAX;
+    int grid = std::min(S, c->num_sms * (use_smem ? std::max<int>(1, (int)(SMEM2_MAX / std::max<size_t>(smem, 1))) : 2));
+    grid = std::min(grid, c->num_sms * 8);
+    double *gwork = nullptr;
+    if (!use_smem) WS(c, "work2d", double, (size_t)grid * per, gwork);
+    if (use_smem) CK(cudaFuncSetAttribute(k_adj2d<NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_MAX));
+    phase_reset(c);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_adj2d<NT2><<<grid, NT2, use_smem ? smem : 0, c->stream>>>(dGF, dG, dU, df, m, n, h, dIX, dJX, S, dSt, gwork, use_smem);
+    LAUNCHED(c, "k_adj2d");
+    double *dSum = nullptr;
+    if (grad_f_sum) {
+        if (loc == ADTOMO_DEVICE) dSum = grad_f_sum;
+        else WS(c, "gfsum", double, N2, dSum);
+        k_sum_sources<<<elem_grid(c, N2), 256, 0, c->stream>>>(dGF, dSum, N2, S);
+        LAUNCHED(c, "k_sum_sources");
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    if (loc == ADTOMO_HOST) {
+        if (grad_f) CK(cudaMemcpyAsync(grad_f, dGF, sizeof(double) * S * N2, cudaMemcpyDeviceToHost, c->stream));
+        if (grad_f_sum) CK(cudaMemcpyAsync(grad_f_sum, dSum, sizeof(double) * N2, cudaMemcpyDeviceToHost, c->stream));
+    }
+    std::vector<int> hs(S);
+    CK(cudaMemcpyAsync(hs.data(), dSt, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < S; s++)
+        if (hs[s] < 0) return ADTOMO_ADJOINT_FLAGGED;
+    return 0;
+}
+
+extern "C" int adtomo_eikonal2d_backward(double *grad_f, const double *grad_u, const double *u, const double *f,
+                                         int m, int n, double h, int ix, int jx) {
+    int rc;
+    adtomo_ctx *c = default_ctx(&rc);
+    if (rc) return rc;
+    return adtomo_eikonal2d_backward_batch(c, grad_f, nullptr, grad_u, u, f, m, n, h, &ix, &jx, 1, ADTOMO_HOST);
+}
+
+// ---------------------------------------------------------------------------------------
+// fused inversion step
+// ---------------------------------------------------------------------------------------
+extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, double *grad_f, const double *f, double h,
+                                            int m, int n, int l, double tol, int max_rounds, int S,
+                                            const int *src_ptr, const int *src_idx, const double *src_val,
+                                            double u0_fill, int E, const double *rcv_xyz, const double *uobs,
+                                            const double *qua, int *rounds, int loc) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "null context");
+    if (!f || !src_ptr || !src_idx || !src_val || !rcv_xyz || !uobs || !qua)
+        return fail(ADTOMO_ERR_ARG, "null input pointer");
+    if (!misfit && !grad_f) return fail(ADTOMO_ERR_ARG, "no output requested");
+    int rc = check_dims3(m, n, l, S);
+    if (rc) return rc;
+    if (E < 1) return fail(ADTOMO_ERR_ARG, "E must be >= 1");
+    if (max_rounds <= 0) max_rounds = 20;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    Dims3 d{m, n, l, (long long)m * n * l};
+    // sparse-source table: the row pointer is needed on the host to size the staging copies
+    std::vector<int> hptr(S + 1);
+    if (loc == ADTOMO_HOST) memcpy(hptr.data(), src_ptr, sizeof(int) * (S + 1));
+    else {
+        CK(cudaMemcpyAsync(hptr.data(), src_ptr, sizeof(int) * (S + 1), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    const int nnz = hptr[S];
+    if (hptr[0] != 0 || nnz < 0) return fail(ADTOMO_ERR_ARG, "src_ptr must start at 0 and be non-decreasing");
+    if (loc == ADTOMO_HOST) {   // validate what we can see
+        for (int q = 0; q < nnz; q++)
+            if (src_idx[q] < 0 || src_idx[q] >= d.N) return fail(ADTOMO_ERR_ARG, "src_idx[%d]=%d outside the grid", q, src_idx[q]);
+        for (int e = 0; e < E; e++) {
+            const double *p = rcv_xyz + 3 * e;
+            if (!(p[0] >= 0 && p[0] <= m - 1 && p[1] >= 0 && p[1] <= n - 1 && p[2] >= 0 && p[2] <= l - 1))
+                return fail(ADTOMO_ERR_ARG, "receiver %d at (%g,%g,%g) outside the grid", e, p[0], p[1], p[2]);
+        }
+    }
+    const double *df, *dval, *drcv, *dobs, *dqua;
+    const int *dptr, *didx;
+    if ((rc = stage_in(c, "f", f, (size_t)d.N, loc, &df))) return rc;
+    if ((rc = stage_in(c, "src_ptr", src_ptr, (size_t)S + 1, loc, &dptr))) return rc;
+    if ((rc = stage_in(c, "src_idx", src_idx, (size_t)std::max(nnz, 1), loc, &didx))) return rc;
+    if ((rc = stage_in(c, "src_val", src_val, (size_t)std::max(nnz, 1), loc, &dval))) return rc;
+    if ((rc = stage_in(c, "rcv", rcv_xyz, (size_t)3 * E, loc, &drcv))) return rc;
+    if ((rc = stage_in(c, "uobs", uobs, (size_t)S * E, loc, &dobs))) return rc;
+    if ((rc = stage_in(c, "qua", qua, (size_t)S * E, loc, &dqua))) return rc;
+
+    // per-source device footprint: U, U0, G, X (8 B each) + code (1 B)
+    int Sc;
+    {
+        size_t per = (size_t)d.N * (4 * sizeof(double) + 1);
+        size_t budget = (size_t)(free_bytes() * 0.8);
+        for (auto &kv : c->ws) budget += kv.second.second;   // what we already hold is reusable
+        Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
+    }
+    double *dU, *dU0, *dG = nullptr, *dMis, *dSum = nullptr, *dSumChunk = nullptr;
+    int *dR, *dSt;
+    WS(c, "U", double, (size_t)Sc * d.N, dU);
+    WS(c, "U0", double, (size_t)Sc * d.N, dU0);
+    WS(c, "mis", double, S, dMis);
+    WS(c, "rounds", int, S, dR);
+    WS(c, "status", int, S, dSt);
+    if (grad_f) {
+        WS(c, "G", double, (size_t)Sc * d.N, dG);
+        if (loc == ADTOMO_DEVICE) dSum = grad_f;
+        else WS(c, "gfsum", double, d.N + 1, dSum);
+        if (Sc < S) {
+            WS(c, "gfsum_chunk", double, d.N, dSumChunk);
+            CK(cudaMemsetAsync(dSum, 0, sizeof(double) * d.N, c->stream));
+        }
+    }
+    CK(cudaMemsetAsync(dMis, 0, sizeof(double) * S, c->stream));
+    CK(cudaMemsetAsync(dSt, 0, sizeof(int) * S, c->stream));
+    phase_reset(c);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int s0 = 0; s0 < S; s0 += Sc) {
+        const int sc = std::min(Sc, S - s0);
+        const long long cnt = (long long)sc * d.N;
+        k_fill<<<elem_grid(c, cnt), 256, 0, c->stream>>>(dU0, cnt, u0_fill);
+        LAUNCHED(c, "k_fill");
+        k_scatter_sources<<<(sc + 127) / 128, 128, 0, c->stream>>>(dU0, dptr + s0, didx, dval, d.N, sc);
+        LAUNCHED(c, "k_scatter_sources");
+        CK(cudaMemcpyAsync(dU, dU0, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, c->stream));
+        if ((rc = fwd3d_device(c, dU, df, d, h, tol, max_rounds, sc, dR + s0, nullptr))) return rc;
+        if (grad_f) CK(cudaMemsetAsync(dG, 0, sizeof(double) * cnt, c->stream));
+        dim3 g((E + 127) / 128, sc);
+        int pkm = phase_begin(c, PH_MISFIT);
+        k_misfit<128><<<g, 128, 0, c->stream>>>(dU, dG, drcv, dobs + (size_t)s0 * E, dqua + (size_t)s0 * E, dMis + s0, d, E,
+                                                 grad_f ? 1 : 0);
+        phase_end(c, pkm);
+        LAUNCHED(c, "k_misfit");
+        if (grad_f) {
+            double *target = (Sc < S) ? dSumChunk : dSum;
+            if ((rc = adj3d_device(c, dU, dU0, dG, df, nullptr, nullptr, target, d, h, sc, dSt + s0))) return rc;
+            if (Sc < S) {
+                k_axpy<<<elem_grid(c, d.N), 256, 0, c->stream>>>(dSum, dSumChunk, d.N);
+                LAUNCHED(c, "k_axpy");
+            }
+        }
+    }
+    // total misfit = sum over sources, fixed order, into dSum[N] when a gradient buffer exists
+    double *dTot;
+    WS(c, "mis_total", double, 1, dTot);
+    k_sum_sources<<<1, 32, 0, c->stream>>>(dMis, dTot, 1, S);
+    LAUNCHED(c, "k_sum_sources");
+    if (grad_f) CK(cudaMemcpyAsync(dSum + d.N, dTot, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    if (grad_f && loc == ADTOMO_HOST)
+        CK(cudaMemcpyAsync(grad_f, dSum, sizeof(double) * (d.N + 1), cudaMemcpyDeviceToHost, c->stream));
+    double hm = 0.0;
+    CK(cudaMemcpyAsync(&hm, dTot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int> hr(S), hs(S);
+    CK(cudaMemcpyAsync(hr.data(), dR, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(hs.data(), dSt, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (misfit) *misfit = hm;
+    int st = rounds_status(hr, rounds);
+    if (grad_f)
+        for (int s = 0; s < S; s++)
+            if (hs[s] < 0) return ADTOMO_ADJOINT_FLAGGED;
+    return st;
+}

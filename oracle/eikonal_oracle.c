@@ -1,0 +1,318 @@
+/*
+ * oracle/eikonal_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, single-threaded CPU restatement of the reference algorithm for the
+ * Eikonal hot path of AI4EPS/ADTomo.jl.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this file.  The
+ * shipped library (adtomo.jl_b200/csrc) never links, calls or falls back to it.
+ *
+ * What each function follows (paths relative to the reference checkout):
+ *   o2_solution / o2_sweep / oracle_eikonal2d_forward
+ *        deps/CustomOps/Eikonal/Eikonal.h:14-20, :22-52, :54-93
+ *   oracle_eikonal2d_backward        deps/CustomOps/Eikonal/Eikonal.h:95-200
+ *   o3_solution                      deps/CustomOps/Eikonal3D/Eikonal3D.cpp:11-28
+ *   o3_sweep / oracle_eikonal3d_forward
+ *        deps/CustomOps/Eikonal3D/Eikonal3D.cpp:35-57, :59-68, :71-94
+ *   oracle_eikonal3d_backward        deps/CustomOps/Eikonal3D/Eikonal3D.cpp:96-198
+ *
+ * The forward solvers are restated operation by operation (same association of
+ * every floating-point expression, same loop order, same stopping rule) and
+ * must be compiled WITHOUT fused multiply-add contraction (-ffp-contract=off),
+ * as the reference is built for generic x86-64 (deps/CustomOps/CMakeLists.txt:47).
+ *
+ * The adjoint: the reference assembles A (rows = linearised Godunov residuals)
+ * and solves A^T x = grad_u with Eigen::SparseLU.  Eigen is a third-party,
+ * un-vendored, unpinned dependency (picked up from ADCME's prefix)
+ * and is absent here.  A^T is a symmetric permutation of a triangular matrix
+ * (a child always has strictly larger travel time than its upwind parent), so
+ * we apply the same assembly rules and solve by exact back-substitution in
+ * decreasing-u order.  tests/ cross-check this against scipy's SuperLU on the
+ * explicitly assembled matrix and against finite differences.
+ *
+ * PARITY PINNING: the reference stores no golden vectors for this path
+ * (SURVEY 4, 8c).  Forward semantics are pinned against the reference's own
+ * Python statements of the same sweeps (tests/Eikonal3D/prototype.py,
+ * tests/Eikonal3D/prototype2d.py; fixtures in tests/golden made by
+ * tests/golden/make_golden.py); the adjoint is pinned against SuperLU + FD.
+ * The reference C++ itself cannot be compiled here (needs Eigen + TensorFlow).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ 2D -- */
+
+/* Eikonal.h:14-20 */
+static double o2_solution(double a, double b, double f, double h) {
+    double d = fabs(a - b);
+    if (d >= f * h) return (b < a ? b : a) + f * h;           /* std::min(a,b) */
+    return (a + b + sqrt(2 * f * f * h * h - (a - b) * (a - b))) / 2;
+}
+
+/* Eikonal.h:22-52.  di/dj = +1 ascending, -1 descending; i is the OUTER loop. */
+static void o2_sweep(double *u, int di, int dj, const double *f, int m, int n,
+                     double h, int ix, int jx) {
+    int w = m + 1;
+    for (int ii = 0; ii <= m; ii++) {
+        int i = di > 0 ? ii : m - ii;
+        for (int jj = 0; jj <= n; jj++) {
+            int j = dj > 0 ? jj : n - jj;
+            if (i == ix && j == jx) continue;
+            double a, b;
+            if (i == 0) a = u[j * w + 1];
+            else if (i == m) a = u[j * w + m - 1];
+            else { double p = u[j * w + i + 1], q = u[j * w + i - 1]; a = q < p ? q : p; }
+            if (j == 0) b = u[w + i];
+            else if (j == n) b = u[(n - 1) * w + i];
+            else { double p = u[(j - 1) * w + i], q = u[(j + 1) * w + i]; b = q < p ? q : p; }
+            double un = o2_solution(a, b, f[j * w + i], h);
+            double uo = u[j * w + i];
+            u[j * w + i] = un < uo ? un : uo;                   /* std::min(u,u_new) */
+        }
+    }
+}
+
+/* Eikonal.h:54-93.  Returns the number of 4-sweep rounds executed; *converged
+ * says whether the relative-L2 test passed (the reference prints an error and
+ * returns the field anyway when it does not). */
+int oracle_eikonal2d_forward(double *u, const double *f, int m, int n, double h,
+                             int ix, int jx, int *converged) {
+    int N = (m + 1) * (n + 1);
+    for (int i = 0; i < m + 1; i++)
+        for (int j = 0; j < n + 1; j++) {
+            u[j * (m + 1) + i] = 100000.0;
+            if (i == ix && j == jx) u[j * (m + 1) + i] = 0.0;
+        }
+    double *uo = (double *)malloc(sizeof(double) * N);
+    memcpy(uo, u, sizeof(double) * N);
+    int conv = 0, it;
+    for (it = 0; it < 100; it++) {
+        o2_sweep(u, +1, +1, f, m, n, h, ix, jx);
+        o2_sweep(u, -1, +1, f, m, n, h, ix, jx);
+        o2_sweep(u, -1, -1, f, m, n, h, ix, jx);
+        o2_sweep(u, +1, -1, f, m, n, h, ix, jx);
+        double num = 0.0, den = 0.0;      /* (u-uold).norm()/uold.norm() */
+        for (int q = 0; q < N; q++) {
+            double d = u[q] - uo[q];
+            num += d * d;
+            den += uo[q] * uo[q];
+        }
+        double err = sqrt(num) / sqrt(den);
+        if (err < 1e-8) { conv = 1; it++; break; }
+        memcpy(uo, u, sizeof(double) * N);
+    }
+    free(uo);
+    if (converged) *converged = conv;
+    return it;
+}
+
+typedef struct { double u; int id; } ukey;
+static int cmp_desc(const void *a, const void *b) {
+    double ua = ((const ukey *)a)->u, ub = ((const ukey *)b)->u;
+    if (ua > ub) return -1;
+    if (ua < ub) return 1;
+    int ia = ((const ukey *)a)->id, ib = ((const ukey *)b)->id;
+    return ia < ib ? -1 : (ia > ib);
+}
+
+/* Eikonal.h:95-200.  Row `src` is the identity; every other row i has, per
+ * axis, parent = the smaller neighbour (mirror at the edges; interior tie ->
+ * the +1 neighbour because the test is u[+1] > u[-1] ? -1 : +1), active iff
+ * u_i > u_parent, diag += 2(u_i-a), A[i,parent] += 2(a-u_i).  Solve A^T x =
+ * grad_u, grad_f = -x * dFdf, dFdf = -2 f h h, dFdf[src] = 0.
+ * Returns 0, or 1 if some non-source row is empty (the reference would hand a
+ * singular matrix to SparseLU; we return x = 0 there). */
+int oracle_eikonal2d_backward(double *grad_f, const double *grad_u,
+                              const double *u, const double *f, int m, int n,
+                              double h, int ix, int jx) {
+    int w = m + 1, N = (m + 1) * (n + 1), singular = 0;
+    int *par = (int *)malloc(sizeof(int) * 2 * N);     /* parent index per axis or -1 */
+    double *alp = (double *)malloc(sizeof(double) * 2 * N);
+    double *acc = (double *)calloc(N, sizeof(double));
+    double *x = (double *)calloc(N, sizeof(double));
+    ukey *ord = (ukey *)malloc(sizeof(ukey) * N);
+    for (int j = 0; j <= n; j++)
+        for (int i = 0; i <= m; i++) {
+            int id = j * w + i;
+            ord[id].u = u[id]; ord[id].id = id;
+            par[2 * id] = par[2 * id + 1] = -1;
+            alp[2 * id] = alp[2 * id + 1] = 0.0;
+            if (i == ix && j == jx) continue;
+            int p;
+            if (i == 0) p = j * w + 1;
+            else if (i == m) p = j * w + m - 1;
+            else p = u[j * w + i + 1] > u[j * w + i - 1] ? j * w + i - 1 : j * w + i + 1;
+            if (u[id] > u[p]) { par[2 * id] = p; alp[2 * id] = 2 * (u[id] - u[p]); }
+            if (j == 0) p = w + i;
+            else if (j == n) p = (n - 1) * w + i;
+            else p = u[(j + 1) * w + i] > u[(j - 1) * w + i] ? (j - 1) * w + i : (j + 1) * w + i;
+            if (u[id] > u[p]) { par[2 * id + 1] = p; alp[2 * id + 1] = 2 * (u[id] - u[p]); }
+        }
+    qsort(ord, N, sizeof(ukey), cmp_desc);
+    int src = jx * w + ix;
+    for (int q = 0; q < N; q++) {
+        int id = ord[q].id;
+        if (id == src) continue;                      /* handled last */
+        double D = alp[2 * id] + alp[2 * id + 1];
+        if (D == 0.0) { singular = 1; x[id] = 0.0; continue; }
+        x[id] = (grad_u[id] + acc[id]) / D;
+        for (int a = 0; a < 2; a++)
+            if (par[2 * id + a] >= 0) acc[par[2 * id + a]] += alp[2 * id + a] * x[id];
+    }
+    x[src] = grad_u[src] + acc[src];
+    for (int id = 0; id < N; id++) {
+        double dFdf = -2 * f[id] * h * h;
+        if (id == src) dFdf = 0.0;
+        grad_f[id] = -x[id] * dFdf;
+    }
+    free(par); free(alp); free(acc); free(x); free(ord);
+    return singular;
+}
+
+/* ------------------------------------------------------------------ 3D -- */
+
+/* Eikonal3D.cpp:11-28 */
+static double o3_solution(double a1_, double a2_, double a3_, double f, double h) {
+    double a1 = a1_, a2 = a2_, a3 = a3_, temp;
+    if (a1 > a2) { temp = a1; a1 = a2; a2 = temp; }
+    if (a1 > a3) { temp = a1; a1 = a3; a3 = temp; }
+    if (a2 > a3) { temp = a2; a2 = a3; a3 = temp; }
+    double x = a1 + f * h;
+    if (x <= a2) return x;
+    double B = -(a1 + a2);
+    double C = (a1 * a1 + a2 * a2 - f * f * h * h) / 2.0;
+    x = (-B + sqrt(B * B - 4 * C)) / 2.0;
+    if (x <= a3) return x;
+    B = -2.0 * (a1 + a2 + a3) / 3.0;
+    C = (a1 * a1 + a2 * a2 + a3 * a3 - f * f * h * h) / 3.0;
+    x = (-B + sqrt(B * B - 4 * C)) / 2.0;
+    return x;
+}
+
+#define ID3(i, j, k) (((size_t)(i) * n + (j)) * l + (k))
+static inline double dmin(double a, double b) { return b < a ? b : a; } /* std::min(a,b) */
+
+/* Eikonal3D.cpp:35-57 */
+static void o3_sweep(double *u, const double *f, double h, int m, int n, int l,
+                     int di, int dj, int dk) {
+    for (int ii = 0; ii < m; ii++) {
+        int i = di > 0 ? ii : m - 1 - ii;
+        for (int jj = 0; jj < n; jj++) {
+            int j = dj > 0 ? jj : n - 1 - jj;
+            for (int kk = 0; kk < l; kk++) {
+                int k = dk > 0 ? kk : l - 1 - kk;
+                double ux = i == 0 ? u[ID3(i + 1, j, k)]
+                          : (i == m - 1 ? u[ID3(i - 1, j, k)]
+                                        : dmin(u[ID3(i + 1, j, k)], u[ID3(i - 1, j, k)]));
+                double uy = j == 0 ? u[ID3(i, j + 1, k)]
+                          : (j == n - 1 ? u[ID3(i, j - 1, k)]
+                                        : dmin(u[ID3(i, j + 1, k)], u[ID3(i, j - 1, k)]));
+                double uz = k == 0 ? u[ID3(i, j, k + 1)]
+                          : (k == l - 1 ? u[ID3(i, j, k - 1)]
+                                        : dmin(u[ID3(i, j, k + 1)], u[ID3(i, j, k - 1)]));
+                double un = o3_solution(ux, uy, uz, f[ID3(i, j, k)], h);
+                u[ID3(i, j, k)] = dmin(un, u[ID3(i, j, k)]);
+            }
+        }
+    }
+}
+
+static const int O3_DIRS[8][3] = {      /* Eikonal3D.cpp:59-68 */
+    {1, 1, 1}, {-1, 1, 1}, {-1, -1, 1}, {1, -1, 1},
+    {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, -1}};
+
+/* One single directional sweep, exposed so that tests can compare iterates
+ * sweep by sweep. */
+void oracle_eikonal3d_sweep(double *u, const double *f, double h, int m, int n,
+                            int l, int sweep_id) {
+    const int *d = O3_DIRS[sweep_id & 7];
+    o3_sweep(u, f, h, m, n, l, d[0], d[1], d[2]);
+}
+
+/* Eikonal3D.cpp:71-94.  max_rounds = 20 reproduces the reference; tests may
+ * lift it to reach the bitwise fixed point.  Returns the rounds executed and
+ * the last L-inf change in *last_err. */
+int oracle_eikonal3d_forward(double *u, const double *u0, const double *f,
+                             double h, int m, int n, int l, double tol,
+                             int verbose, int max_rounds, double *last_err) {
+    size_t N = (size_t)m * n * l;
+    memcpy(u, u0, sizeof(double) * N);
+    double *uo = (double *)malloc(sizeof(double) * N);
+    int it = 0;
+    double err = 0.0;
+    for (int i = 0; i < max_rounds; i++) {
+        memcpy(uo, u, sizeof(double) * N);
+        for (int s = 0; s < 8; s++)
+            o3_sweep(u, f, h, m, n, l, O3_DIRS[s][0], O3_DIRS[s][1], O3_DIRS[s][2]);
+        err = 0.0;
+        for (size_t j = 0; j < N; j++) {
+            double d = fabs(u[j] - uo[j]);
+            err = d > err ? d : err;                    /* std::max(fabs(..), err) */
+        }
+        if (verbose) printf("Iteration %d, Error = %0.6e\n", i, err);
+        it = i + 1;
+        if (err < tol) break;
+    }
+    free(uo);
+    if (last_err) *last_err = err;
+    return it;
+}
+
+/* Eikonal3D.cpp:96-198, solved by back-substitution (see header).
+ * Returns the number of pinned nodes. */
+int oracle_eikonal3d_backward(double *grad_u0, double *grad_f,
+                              const double *grad_u, const double *u,
+                              const double *u0, const double *f, double h,
+                              int m, int n, int l) {
+    size_t N = (size_t)m * n * l;
+    int *par = (int *)malloc(sizeof(int) * 3 * N);
+    double *alp = (double *)malloc(sizeof(double) * 3 * N);
+    double *acc = (double *)calloc(N, sizeof(double));
+    double *x = (double *)calloc(N, sizeof(double));
+    char *pin = (char *)calloc(N, 1);
+    ukey *ord = (ukey *)malloc(sizeof(ukey) * N);
+    int npin = 0;
+    for (size_t q = 0; q < N; q++)                       /* :106-110 */
+        grad_u0[q] = (u[q] == u0[q]) ? grad_u[q] : 0.0;
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < n; j++)
+            for (int k = 0; k < l; k++) {
+                size_t id = ID3(i, j, k);
+                ord[id].u = u[id]; ord[id].id = (int)id;
+                for (int a = 0; a < 3; a++) { par[3 * id + a] = -1; alp[3 * id + a] = 0.0; }
+                if (u[id] == u0[id]) { pin[id] = 1; npin++; continue; }   /* :126-130 */
+                size_t p[3];
+                p[0] = i == 0 ? ID3(i + 1, j, k) : (i == m - 1 ? ID3(i - 1, j, k)
+                     : (u[ID3(i + 1, j, k)] > u[ID3(i - 1, j, k)] ? ID3(i - 1, j, k) : ID3(i + 1, j, k)));
+                p[1] = j == 0 ? ID3(i, j + 1, k) : (j == n - 1 ? ID3(i, j - 1, k)
+                     : (u[ID3(i, j + 1, k)] > u[ID3(i, j - 1, k)] ? ID3(i, j - 1, k) : ID3(i, j + 1, k)));
+                p[2] = k == 0 ? ID3(i, j, k + 1) : (k == l - 1 ? ID3(i, j, k - 1)
+                     : (u[ID3(i, j, k + 1)] > u[ID3(i, j, k - 1)] ? ID3(i, j, k - 1) : ID3(i, j, k + 1)));
+                int any = 0;
+                for (int a = 0; a < 3; a++)
+                    if (u[id] > u[p[a]]) {                 /* :149-165 */
+                        any = 1;
+                        par[3 * id + a] = (int)p[a];
+                        alp[3 * id + a] = 2.0 * (u[id] - u[p[a]]);
+                    }
+                if (!any) { pin[id] = 1; npin++; }       /* :168-171 */
+            }
+    qsort(ord, N, sizeof(ukey), cmp_desc);
+    for (size_t q = 0; q < N; q++) {
+        int id = ord[q].id;
+        if (pin[id]) { x[id] = 0.0; continue; }        /* rows/cols of Z zeroed, g_Z = 0 */
+        double D = alp[3 * id] + alp[3 * id + 1] + alp[3 * id + 2];
+        x[id] = (grad_u[id] + acc[id]) / D;
+        for (int a = 0; a < 3; a++) {
+            int p = par[3 * id + a];
+            if (p >= 0 && !pin[p]) acc[p] += alp[3 * id + a] * x[id];
+        }
+    }
+    for (size_t q = 0; q < N; q++) {
+        double rhs = -2 * f[q] * h * h;                 /* :113-116 */
+        grad_f[q] = -x[q] * rhs;                        /* :194-196 */
+    }
+    free(par); free(alp); free(acc); free(x); free(pin); free(ord);
+    return npin;
+}
