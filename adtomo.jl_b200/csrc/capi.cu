@@ -13,6 +13,7 @@
 
 #include "../../include/adtomo_b200.h"
 #include "kernels_v0.cuh"
+#include "kernels_adj_topo.cuh"
 
 using namespace adtomo;
 
@@ -233,29 +234,37 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
                         double *dGU0, double *dGF, double *dGFsum, const Dims3 &d, double h, int S,
                         int *d_status) {
     double *X;
-    unsigned char *code;
-    int *rem;
-    WS(c, "adj_x", double, (size_t)S * d.N, X);
-    WS(c, "adj_code", unsigned char, (size_t)S * d.N, code);
-    WS(c, "adj_rem", int, S, rem);
-    CK(cudaMemsetAsync(rem, 0, sizeof(int) * S, c->stream));
+    unsigned char *code, *cnt;
+    int *Q, *cnts;   // cnts: [0,S) number of non-pinned nodes per source, [S,2S) ready-queue tails
+    const size_t total = (size_t)S * d.N;
+    WS(c, "adj_x", double, total, X);
+    WS(c, "adj_code", unsigned char, total, code);
+    WS(c, "adj_cnt", unsigned char, (total + 7) & ~(size_t)3, cnt);
+    WS(c, "adj_queue", int, total, Q);
+    WS(c, "adj_counters", int, 3 * (size_t)S, cnts);
+    CK(cudaMemsetAsync(cnts, 0, sizeof(int) * 3 * S, c->stream));
     int pk = phase_begin(c, PH_ADJ_SETUP);
-    k_adj3d_setup<<<elem_grid(c, d.N * S), 256, 0, c->stream>>>(dU, dU0, dG, X, dGU0, code, rem, d, S);
-    phase_end(c, pk);
+    k_adj3d_setup<<<elem_grid(c, d.N * S), 256, 0, c->stream>>>(dU, dU0, dG, X, dGU0, code, cnts, d, S);
     LAUNCHED(c, "k_adj3d_setup");
     if (dGF || dGFsum) {
+        k_adj3d_count<<<elem_grid(c, d.N * S), 256, 0, c->stream>>>(code, cnt, Q, cnts + S, d, S);
+        phase_end(c, pk);
+        LAUNCHED(c, "k_adj3d_count");
         int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_v0<NT3>, NT3, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo<NT3>, NT3, 0));
         if (occ < 1) occ = 1;
         int grid = std::min(S, c->num_sms * occ);
         pk = phase_begin(c, PH_ADJ_SWEEP);
-        k_adj3d_v0<NT3><<<grid, NT3, 0, c->stream>>>(dU, dG, X, code, rem, d, S, 4096, d_status);
+        k_adj3d_topo<NT3><<<grid, NT3, 0, c->stream>>>(dU, dG, X, code, (unsigned int *)cnt, Q, cnts + S, cnts, d,
+                                                        S, d_status);
         phase_end(c, pk);
-        LAUNCHED(c, "k_adj3d_v0");
+        LAUNCHED(c, "k_adj3d_topo");
         pk = phase_begin(c, PH_ADJ_FINISH);
         k_adj3d_finish<<<elem_grid(c, d.N), 256, 0, c->stream>>>(X, df, dGF, dGFsum, d.N, S, h);
         phase_end(c, pk);
         LAUNCHED(c, "k_adj3d_finish");
+    } else {
+        phase_end(c, pk);
     }
     return 0;
 }
@@ -373,7 +382,7 @@ extern "C" int adtomo_eikonal3d_backward_batch(adtomo_ctx *c, double *grad_u0, d
     if ((rc = stage_in(c, "f", f, (size_t)d.N, loc, &df))) return rc;
     int Sc = S;
     {
-        size_t per = sizeof(double) * (size_t)d.N * (loc == ADTOMO_HOST ? 6 : 1) + (size_t)d.N;
+        size_t per = sizeof(double) * (size_t)d.N * (loc == ADTOMO_HOST ? 6 : 1) + (size_t)d.N * 6;
         size_t budget = free_bytes() / 2;
         Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
     }
@@ -623,7 +632,7 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     // per-source device footprint: U, U0, G, X (8 B each) + code (1 B)
     int Sc;
     {
-        size_t per = (size_t)d.N * (4 * sizeof(double) + 1);
+        size_t per = (size_t)d.N * (4 * sizeof(double) + 6);
         size_t budget = (size_t)(free_bytes() * 0.8);
         for (auto &kv : c->ws) budget += kv.second.second;   // what we already hold is reusable
         Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
