@@ -14,6 +14,7 @@
 #include "../../include/adtomo_b200.h"
 #include "kernels_v0.cuh"
 #include "kernels_adj_topo.cuh"
+#include "kernels_fwd_v1.cuh"
 
 using namespace adtomo;
 
@@ -48,9 +49,19 @@ struct adtomo_ctx {
     // per-phase device timing of the last call: pairs of events around the kernels of each phase
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     std::vector<std::pair<int, int>> ev_used;   // (phase, pool index)
+    std::vector<struct PlanCache *> plans;      // level-major layout plans, one per grid shape
+    int force_v0 = 0;                           // debugging aid: ADTOMO_FORCE_V0=1 selects the row-major kernel
 };
 
-enum { PH_FWD = 0, PH_MISFIT = 1, PH_ADJ_SETUP = 2, PH_ADJ_SWEEP = 3, PH_ADJ_FINISH = 4, PH_COUNT = 5 };
+struct PlanCache {
+    int m, n, l;
+    HostPlan hp;
+    Plan3 dev;          // same as hp.plan but with DEVICE table pointers
+    int *d_tables = nullptr;
+    size_t smem_bytes = 0;
+};
+
+enum { PH_FWD = 0, PH_MISFIT = 1, PH_ADJ_SETUP = 2, PH_ADJ_SWEEP = 3, PH_ADJ_FINISH = 4, PH_CONVERT = 5, PH_COUNT = 6 };
 
 static void phase_reset(adtomo_ctx *c) { c->ev_used.clear(); }
 static int phase_begin(adtomo_ctx *c, int phase) {
@@ -119,6 +130,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    const char *fv0 = getenv("ADTOMO_FORCE_V0");
+    c->force_v0 = (fv0 && fv0[0] == '1');
     *out = c;
     return 0;
 }
@@ -129,6 +142,10 @@ extern "C" int adtomo_destroy(adtomo_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (auto &kv : c->ws)
         if (kv.second.first) cudaFree(kv.second.first);
+    for (auto *pc : c->plans) {
+        if (pc->d_tables) cudaFree(pc->d_tables);
+        delete pc;
+    }
     for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -215,8 +232,74 @@ static size_t free_bytes() {
 // ---------------------------------------------------------------------------------------
 static constexpr int NT3 = 512;
 
+static constexpr int NT1 = 1024;
+static constexpr size_t SMEM_MAX_DYN = 227 * 1024 - 2048;
+
+static int get_plan(adtomo_ctx *c, int m, int n, int l, PlanCache **out) {
+    for (auto *pc : c->plans)
+        if (pc->m == m && pc->n == n && pc->l == l) { *out = pc; return 0; }
+    PlanCache *pc = new PlanCache();
+    pc->m = m; pc->n = n; pc->l = l;
+    if (!build_plan(pc->hp, m, n, l)) { delete pc; return fail(ADTOMO_ERR_ARG, "internal: layout plan construction failed for %dx%dx%d", m, n, l); }
+    size_t total = 0;
+    for (int q = 0; q < NLAYOUT; q++) total += pc->hp.lay[q].levelStart.size() + pc->hp.lay[q].rowStart.size();
+    std::vector<int> host(total);
+    CK(cudaMalloc(&pc->d_tables, sizeof(int) * total));
+    pc->dev = pc->hp.plan;
+    size_t o = 0;
+    for (int q = 0; q < NLAYOUT; q++) {
+        auto &H = pc->hp.lay[q];
+        memcpy(&host[o], H.levelStart.data(), sizeof(int) * H.levelStart.size());
+        pc->dev.lay[q].levelStart = pc->d_tables + o;
+        o += H.levelStart.size();
+        memcpy(&host[o], H.rowStart.data(), sizeof(int) * H.rowStart.size());
+        pc->dev.lay[q].rowStart = pc->d_tables + o;
+        o += H.rowStart.size();
+    }
+    CK(cudaMemcpy(pc->d_tables, host.data(), sizeof(int) * total, cudaMemcpyHostToDevice));
+    pc->smem_bytes = sizeof(double) * 2 * (size_t)pc->dev.sheet;
+    c->plans.push_back(pc);
+    *out = pc;
+    return 0;
+}
+
+// dU: S x N row-major, holds u0 on entry and the travel times on exit.
 static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3 &d, double h, double tol,
                         int max_rounds, int S, int *d_rounds, double *d_errs) {
+    PlanCache *pc = nullptr;
+    int rc = get_plan(c, d.m, d.n, d.l, &pc);
+    if (rc) return rc;
+    if (!c->force_v0 && pc->smem_bytes <= SMEM_MAX_DYN) {
+        // level-major path: convert in, sweep, convert out
+        double *bufs, *flay;
+        int *where;
+        WS(c, "fwd_bufs", double, (size_t)S * 3 * d.N, bufs);
+        WS(c, "fwd_flay", double, (size_t)NLAYOUT * d.N, flay);
+        WS(c, "fwd_where", int, S, where);
+        static bool attr_set = false;
+        if (!attr_set) {
+            CK(cudaFuncSetAttribute(k_fwd3d_v1<NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
+            attr_set = true;
+        }
+        int pk = phase_begin(c, PH_CONVERT);
+        const int eb = elem_grid(c, d.N);
+        k_f_to_layouts<<<eb, 256, 0, c->stream>>>(pc->dev, df, flay);
+        LAUNCHED(c, "k_f_to_layouts");
+        k_u0_to_L0<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(pc->dev, dU, bufs);
+        phase_end(c, pk);
+        LAUNCHED(c, "k_u0_to_L0");
+        int grid = std::min(S, c->num_sms);
+        pk = phase_begin(c, PH_FWD);
+        k_fwd3d_v1<NT1><<<grid, NT1, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds,
+                                                                 d_errs, where);
+        phase_end(c, pk);
+        LAUNCHED(c, "k_fwd3d_v1");
+        pk = phase_begin(c, PH_CONVERT);
+        k_L0_to_rowmajor<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(pc->dev, bufs, where, dU);
+        phase_end(c, pk);
+        LAUNCHED(c, "k_L0_to_rowmajor");
+        return 0;
+    }
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fwd3d_v0<NT3>, NT3, 0));
     if (occ < 1) occ = 1;
@@ -301,7 +384,7 @@ extern "C" int adtomo_eikonal3d_forward_batch(adtomo_ctx *c, double *u, const do
     // chunk the sources so that host-staged batches fit the device
     int Sc = S;
     if (loc == ADTOMO_HOST) {
-        size_t per = sizeof(double) * (size_t)d.N * 2;
+        size_t per = sizeof(double) * (size_t)d.N * 4;
         size_t budget = free_bytes() / 2;
         Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
     }
@@ -632,7 +715,7 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     // per-source device footprint: U, U0, G, X (8 B each) + code (1 B)
     int Sc;
     {
-        size_t per = (size_t)d.N * (4 * sizeof(double) + 6);
+        size_t per = (size_t)d.N * (7 * sizeof(double) + 6);
         size_t budget = (size_t)(free_bytes() * 0.8);
         for (auto &kv : c->ws) budget += kv.second.second;   // what we already hold is reusable
         Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));

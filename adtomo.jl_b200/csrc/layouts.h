@@ -1,0 +1,174 @@
+// layouts.h -- hyperplane-major ("level-set major") storage layouts for the 3D sweeps.
+//
+// A directional Gauss-Seidel sweep (Eikonal3D.cpp:35-57) can be executed level by level, a level
+// being the set of nodes with  c_i + c_j + c_k = lambda  where c_a is the coordinate along axis a
+// counted in the sweep's direction.  The 8 sweeps of a round (Eikonal3D.cpp:59-68) use 4 families
+// of level sets (a sweep and its reverse share one).  In the reference's row-major layout a level
+// is a diagonal cut (stride l-1 doubles): every access is a separate 32-byte sector.  Internally
+// we therefore store a field LEVEL BY LEVEL: all nodes of level 0, then level 1, ...; inside a
+// level, rows of constant "major" coordinate A, and inside a row ascending "minor" coordinate B
+// (the third, "derived" coordinate is C = lambda - A - B).  A whole level is one contiguous block
+// and a sweep streams it exactly once.
+//
+// Consecutive sweeps of the reference's order differ in the sign of exactly ONE axis (Gray code),
+// and the intersection of a level of sweep P with a level of the next sweep X is a grid line with
+// that axis fixed.  If X's layout uses that axis as its major axis, every such line is a full,
+// contiguous row of X's layout, so sweep P can write its result straight into X's layout with
+// coalesced stores.  That fixes 5 layouts (family, major axis):
+//    L0 = (+,+,+ | j)  L1 = (-,+,+ | i)  L2 = (-,-,+ | j)  L3 = (+,-,+ | i)  L4 = (-,+,+ | k)
+// and the schedule  sw1: L0->L1, sw2: L1->L2, sw3: L2->L3, sw4: L3->L4, sw5: L4->L2 (reverse),
+// sw6: L2->L3 (rev), sw7: L3->L0 (rev), sw8: L0->L0 (rev).
+// The C ABI keeps the reference's row-major layout; these layouts never leave the library.
+#pragma once
+#include <cstdlib>
+#include <vector>
+
+namespace adtomo {
+
+constexpr int NLAYOUT = 5;
+
+struct LayoutDev {
+    int ax0, ax1, ax2;   // physical axis (0=i,1=j,2=k) of the major / minor / derived coordinate
+    int flip[3];         // per PHYSICAL axis: canonical coordinate = ext-1-x when 1
+    int dA, dB, dC;      // extents along major / minor / derived
+    int nlev;            // dA+dB+dC-2
+    int pitch;           // row pitch of the shared-memory sheet (>= dB, == 2 mod 4)
+    const int *levelStart;   // [nlev+1]   offset of a level in the field
+    const int *rowStart;     // [nlev*dA]  offset of row A inside its level
+};
+
+struct SweepDev {
+    int rl, wl, dir;          // layout read, layout written, +1 ascending / -1 descending levels
+    int sh0, shL, shV, shT;   // write phase: sheet address of X-row v, X-minor t:  sh0+shL*lam+shV*v+shT*t
+    int lx0, lxL, lxV;        // write phase: X level  lamX = lx0 + lxL*lam + lxV*v
+};
+
+struct Plan3 {
+    int ext[3];
+    int N;
+    int sheet;            // doubles per shared-memory sheet (max over layouts of dA*pitch)
+    LayoutDev lay[NLAYOUT];
+    SweepDev sw[8];
+};
+
+#if defined(__CUDACC__)
+#define LAY_HD __host__ __device__ __forceinline__
+#else
+#define LAY_HD inline
+#endif
+
+LAY_HD int lay_imax(int a, int b) { return a > b ? a : b; }
+LAY_HD int lay_imin(int a, int b) { return a < b ? a : b; }
+
+// offset of physical node (x[0],x[1],x[2]) in layout L
+LAY_HD int lay_offset(const LayoutDev &L, const int *ext, int xi, int xj, int xk) {
+    const int x[3] = {xi, xj, xk};
+    const int A = L.flip[L.ax0] ? ext[L.ax0] - 1 - x[L.ax0] : x[L.ax0];
+    const int B = L.flip[L.ax1] ? ext[L.ax1] - 1 - x[L.ax1] : x[L.ax1];
+    const int C = L.flip[L.ax2] ? ext[L.ax2] - 1 - x[L.ax2] : x[L.ax2];
+    const int lam = A + B + C;
+    const int Blo = lay_imax(0, lam - A - (L.dC - 1));
+    return L.levelStart[lam] + L.rowStart[lam * L.dA + A] + (B - Blo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side construction
+// ---------------------------------------------------------------------------------------------
+struct HostLayout {
+    LayoutDev d;                  // levelStart/rowStart point into the vectors below
+    std::vector<int> levelStart, rowStart;
+};
+
+inline void build_layout(HostLayout &H, const int ext[3], const int sign[3], int major) {
+    LayoutDev &L = H.d;
+    int o1 = (major + 1) % 3, o2 = (major + 2) % 3;
+    if (o1 > o2) { int t = o1; o1 = o2; o2 = t; }
+    // minor = the smaller extent of the two remaining axes (tie: the later axis)
+    int minor = (ext[o1] < ext[o2]) ? o1 : o2;
+    int derived = (minor == o1) ? o2 : o1;
+    L.ax0 = major; L.ax1 = minor; L.ax2 = derived;
+    for (int a = 0; a < 3; a++) L.flip[a] = sign[a] < 0;
+    L.dA = ext[major]; L.dB = ext[minor]; L.dC = ext[derived];
+    L.nlev = L.dA + L.dB + L.dC - 2;
+    int p = L.dB;
+    while ((p & 3) != 2) p++;
+    L.pitch = p;
+    H.levelStart.assign(L.nlev + 1, 0);
+    H.rowStart.assign((size_t)L.nlev * L.dA, 0);
+    int acc = 0;
+    for (int lam = 0; lam < L.nlev; lam++) {
+        H.levelStart[lam] = acc;
+        int racc = 0;
+        for (int A = 0; A < L.dA; A++) {
+            H.rowStart[(size_t)lam * L.dA + A] = racc;
+            int t = lam - A;
+            int lo = lay_imax(0, t - (L.dC - 1)), hi = lay_imin(L.dB - 1, t);
+            if (hi >= lo) racc += hi - lo + 1;
+        }
+        acc += racc;
+    }
+    H.levelStart[L.nlev] = acc;
+    L.levelStart = H.levelStart.data();
+    L.rowStart = H.rowStart.data();
+}
+
+struct HostPlan {
+    Plan3 plan;                   // with HOST table pointers
+    HostLayout lay[NLAYOUT];
+    bool ok = false;
+};
+
+// Returns false if some invariant of the construction does not hold (never expected).
+inline bool build_plan(HostPlan &HP, int m, int n, int l) {
+    Plan3 &P = HP.plan;
+    P.ext[0] = m; P.ext[1] = n; P.ext[2] = l;
+    P.N = m * n * l;
+    static const int signs[NLAYOUT][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, 1}};
+    static const int majors[NLAYOUT] = {1, 0, 1, 0, 2};
+    P.sheet = 0;
+    for (int q = 0; q < NLAYOUT; q++) {
+        build_layout(HP.lay[q], P.ext, signs[q], majors[q]);
+        P.lay[q] = HP.lay[q].d;
+        if (HP.lay[q].levelStart.back() != P.N) return false;
+        P.sheet = lay_imax(P.sheet, P.lay[q].dA * P.lay[q].pitch);
+    }
+    static const int sched[8][3] = {{0, 1, 1}, {1, 2, 1}, {2, 3, 1}, {3, 4, 1}, {4, 2, -1}, {2, 3, -1}, {3, 0, -1}, {0, 0, -1}};
+    // reference sweep directions, to double-check the schedule (Eikonal3D.cpp:59-68)
+    static const int dirs[8][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, -1, 1}, {1, -1, 1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, -1}};
+    for (int s = 0; s < 8; s++) {
+        SweepDev &W = P.sw[s];
+        W.rl = sched[s][0]; W.wl = sched[s][1]; W.dir = sched[s][2];
+        const LayoutDev &R = P.lay[W.rl], &X = P.lay[W.wl];
+        for (int a = 0; a < 3; a++)
+            if ((R.flip[a] ? -1 : 1) * W.dir != dirs[s][a]) return false;
+        // c_R[a] = sg[a]*c_X[a] + of[a]
+        int sg[3], of[3], O = 0;
+        for (int a = 0; a < 3; a++) {
+            if (R.flip[a] == X.flip[a]) { sg[a] = 1; of[a] = 0; }
+            else { sg[a] = -1; of[a] = P.ext[a] - 1; }
+            O += of[a];
+        }
+        if (sg[X.ax1] != sg[X.ax2]) return false;   // the X row must lie inside one R level
+        const int sigma = sg[X.ax1];
+        W.lxL = sigma;
+        W.lxV = 1 - sigma * sg[X.ax0];
+        W.lx0 = -sigma * O;
+        auto addr = [&](int lam, int v, int t) {
+            int lamX = W.lx0 + W.lxL * lam + W.lxV * v;
+            int cX[3];
+            cX[X.ax0] = v; cX[X.ax1] = t; cX[X.ax2] = lamX - v - t;
+            int cR[3];
+            for (int a = 0; a < 3; a++) cR[a] = sg[a] * cX[a] + of[a];
+            return cR[R.ax0] * R.pitch + cR[R.ax1];
+        };
+        W.sh0 = addr(0, 0, 0);
+        W.shL = addr(1, 0, 0) - W.sh0;
+        W.shV = addr(0, 1, 0) - W.sh0;
+        W.shT = addr(0, 0, 1) - W.sh0;
+        if (addr(3, 5, 7) != W.sh0 + 3 * W.shL + 5 * W.shV + 7 * W.shT) return false;
+    }
+    HP.ok = true;
+    return true;
+}
+
+}  // namespace adtomo

@@ -251,10 +251,10 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         lc0 = ctx.launch_count
         e0.record()
-        ph = np.zeros(5)
+        ph = np.zeros(6)
         for _ in range(steps):
             fn()
-            ph += [ctx.phase_ms(p) for p in range(5)]
+            ph += [ctx.phase_ms(p) for p in range(6)]
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
@@ -290,7 +290,7 @@ def run_ours(args):
     fwd_ms, adj_ms = phases[0], phases[3]
     kern = {"forward_sweeps": {"ms": fwd_ms, "alg_gb": bf / 1e9, "gbs": bf / 1e6 / max(fwd_ms, 1e-9)},
             "adjoint_sweeps": {"ms": adj_ms, "alg_gb": ba / 1e9, "gbs": ba / 1e6 / max(adj_ms, 1e-9)},
-            "misfit_ms": phases[1], "adjoint_setup_ms": phases[2], "finish_ms": phases[4]}
+            "misfit_ms": phases[1], "adjoint_setup_ms": phases[2], "finish_ms": phases[4], "layout_convert_ms": phases[5]}
     dom = "forward_sweeps" if fwd_ms >= adj_ms else "adjoint_sweeps"
     achieved = kern[dom]["gbs"]
     step_alg_gbs = (bf + ba) / 1e6 / (ms_dev / args.steps)

@@ -57,7 +57,8 @@ unsigned long long adtomo_stream(adtomo_ctx *ctx);
 double adtomo_last_kernel_ms(adtomo_ctx *ctx);
 /* Device time (ms) of one phase of the last call, summed over its launches; CUDA events recorded
  * on the context's stream immediately around the kernels.  phase: 0 = forward sweeps kernel,
- * 1 = receiver sampling/misfit, 2 = adjoint setup, 3 = adjoint sweeps kernel, 4 = gradient finish. */
+ * 1 = receiver sampling/misfit, 2 = adjoint setup, 3 = adjoint wavefront kernel, 4 = gradient finish,
+ * 5 = layout conversions around the forward kernel. */
 double adtomo_last_phase_ms(adtomo_ctx *ctx, int phase);
 /* Number of kernels this library has launched on the context since creation. */
 long long adtomo_launch_count(adtomo_ctx *ctx);
