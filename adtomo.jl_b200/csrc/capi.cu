@@ -242,19 +242,16 @@ static int get_plan(adtomo_ctx *c, int m, int n, int l, PlanCache **out) {
     pc->m = m; pc->n = n; pc->l = l;
     if (!build_plan(pc->hp, m, n, l)) { delete pc; return fail(ADTOMO_ERR_ARG, "internal: layout plan construction failed for %dx%dx%d", m, n, l); }
     size_t total = 0;
-    for (int q = 0; q < NLAYOUT; q++) total += pc->hp.lay[q].levelStart.size() + pc->hp.lay[q].rowStart.size();
+    for (int q = 0; q < NLAYOUT; q++) total += pc->hp.lay[q].rowIndex.size();
     std::vector<int> host(total);
     CK(cudaMalloc(&pc->d_tables, sizeof(int) * total));
     pc->dev = pc->hp.plan;
     size_t o = 0;
     for (int q = 0; q < NLAYOUT; q++) {
         auto &H = pc->hp.lay[q];
-        memcpy(&host[o], H.levelStart.data(), sizeof(int) * H.levelStart.size());
-        pc->dev.lay[q].levelStart = pc->d_tables + o;
-        o += H.levelStart.size();
-        memcpy(&host[o], H.rowStart.data(), sizeof(int) * H.rowStart.size());
-        pc->dev.lay[q].rowStart = pc->d_tables + o;
-        o += H.rowStart.size();
+        memcpy(&host[o], H.rowIndex.data(), sizeof(int) * H.rowIndex.size());
+        pc->dev.lay[q].rowIndex = pc->d_tables + o;
+        o += H.rowIndex.size();
     }
     CK(cudaMemcpy(pc->d_tables, host.data(), sizeof(int) * total, cudaMemcpyHostToDevice));
     pc->smem_bytes = sizeof(double) * 2 * (size_t)pc->dev.sheet;
@@ -273,8 +270,8 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         // level-major path: convert in, sweep, convert out
         double *bufs, *flay;
         int *where;
-        WS(c, "fwd_bufs", double, (size_t)S * 3 * d.N, bufs);
-        WS(c, "fwd_flay", double, (size_t)NLAYOUT * d.N, flay);
+        WS(c, "fwd_bufs", double, (size_t)S * 3 * pc->dev.Mmax, bufs);
+        WS(c, "fwd_flay", double, (size_t)NLAYOUT * pc->dev.Mmax, flay);
         WS(c, "fwd_where", int, S, where);
         static bool attr_set = false;
         if (!attr_set) {
@@ -384,7 +381,7 @@ extern "C" int adtomo_eikonal3d_forward_batch(adtomo_ctx *c, double *u, const do
     // chunk the sources so that host-staged batches fit the device
     int Sc = S;
     if (loc == ADTOMO_HOST) {
-        size_t per = sizeof(double) * (size_t)d.N * 4;
+        size_t per = sizeof(double) * (size_t)d.N * 8;
         size_t budget = free_bytes() / 2;
         Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
     }
@@ -715,7 +712,7 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     // per-source device footprint: U, U0, G, X (8 B each) + code (1 B)
     int Sc;
     {
-        size_t per = (size_t)d.N * (7 * sizeof(double) + 6);
+        size_t per = (size_t)d.N * (10 * sizeof(double) + 6);
         size_t budget = (size_t)(free_bytes() * 0.8);
         for (auto &kv : c->ws) budget += kv.second.second;   // what we already hold is reusable
         Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));

@@ -19,6 +19,8 @@
 
 namespace adtomo {
 
+#define EIK_INF __longlong_as_double(0x7ff0000000000000LL)
+
 template <int NT>
 __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const double *rd, double *wr,
                                            const double *__restrict__ fl, const double *cmp, const double h,
@@ -29,91 +31,78 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
     const int dir = W.dir;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = NT / 32;
-    const int dA = L.dA, dB = L.dB, dC = L.dC, pitch = L.pitch, nlev = L.nlev;
-    const int segs = (min(dB, dC) + 31) >> 5;
-    const int segsX = (min(X.dB, X.dC) + 31) >> 5;
-    const int *__restrict__ lsT = L.levelStart;
-    const int *__restrict__ rsT = L.rowStart;
-    const int *__restrict__ lsX = X.levelStart;
-    const int *__restrict__ rsX = X.rowStart;
+    const int dA = L.dA, dB = L.dB, dC = L.dC, pitch = L.pitch, pg = L.pg, nlev = L.nlev;
+    // segments of 32 minor coordinates per row, rounded up to a power of two (shift/mask, no division)
+    int sl = 0;
+    while ((32 << sl) < dB) sl++;
+    const int smask = (1 << sl) - 1;
+    int slX = 0;
+    while ((32 << slX) < X.dB) slX++;
+    const int smaskX = (1 << slX) - 1;
+    const int TX = X.dB + X.dC - 2;
+    const int kappa = W.lxV - 1;   // tX = lamX0 + kappa*v, kappa = +-1
+    const int *__restrict__ riL = L.rowIndex;
+    const int *__restrict__ riX = X.rowIndex;
+    const int dpg = dir * pg, dpitch = dir * pitch;
     double *shPrev = shA, *shCur = shB;
     for (int step = 0; step < nlev; step++) {
         const int lam = dir > 0 ? step : nlev - 1 - step;
-        // ------------------------------------------------------------------ phase 1
+        // ------------------------------------------------------------------ phase 1: update the level
         {
             const int Alo = max(0, lam - (dB - 1) - (dC - 1)), Ahi = min(dA - 1, lam);
-            const int npairs = (Ahi - Alo + 1) * segs;
+            const int npairs = (Ahi - Alo + 1) << sl;
             const int lamD = lam + dir;
             const bool hasD = (unsigned)lamD < (unsigned)nlev;
-            const int ls = lsT[lam];
-            const int lsD = hasD ? lsT[lamD] : 0;
+            const int base0 = (riL[lam] - Alo) * pg;
+            const int baseD = hasD ? (riL[lamD] - max(0, lamD - (dB - 1) - (dC - 1))) * pg : 0;
             for (int p = warp; p < npairs; p += NW) {
-                const int Ar = p / segs;
-                const int seg = p - Ar * segs;
-                const int A = Alo + Ar;
-                const int t = lam - A;
-                const int Blo = max(0, t - (dC - 1)), Bhi = min(dB - 1, t);
-                const int B = Blo + seg * 32 + lane;
-                if (B > Bhi) continue;
-                const int C = t - B;
-                const int off = ls + rsT[lam * dA + A] + (B - Blo);
-                const double own = rd[off];
-                // upwind neighbours: previous level, shared-memory sheet
-                const int Au = A - dir, Bu = B - dir, Cu = C - dir;
-                const bool hUA = (unsigned)Au < (unsigned)dA, hUB = (unsigned)Bu < (unsigned)dB,
-                           hUC = (unsigned)Cu < (unsigned)dC;
-                // downwind neighbours: next level, global memory (old values)
-                const int Ad = A + dir, Bd = B + dir, Cd = C + dir;
-                const bool hDA = (unsigned)Ad < (unsigned)dA, hDB = (unsigned)Bd < (unsigned)dB,
-                           hDC = (unsigned)Cd < (unsigned)dC;
-                double vA, vB, vC;
-                {
-                    // row A of level lamD holds (A, B+dir, C) at B+dir and (A, B, C+dir) at B
-                    const int tD = lamD - A;
-                    const int BloD = max(0, tD - (dC - 1));
-                    const int rowD = hasD ? lsD + rsT[lamD * dA + A] - BloD : 0;
-                    const double uB = hUB ? shPrev[A * pitch + Bu] : 0.0;
-                    const double uC = hUC ? shPrev[A * pitch + B] : 0.0;
-                    const double dB_ = hDB ? rd[rowD + Bd] : 0.0;
-                    const double dC_ = hDC ? rd[rowD + B] : 0.0;
-                    vB = !hUB ? dB_ : (!hDB ? uB : eik_min(uB, dB_));
-                    vC = !hUC ? dC_ : (!hDC ? uC : eik_min(uC, dC_));
-                    const double uA = hUA ? shPrev[Au * pitch + B] : 0.0;
-                    double dA_ = 0.0;
-                    if (hDA) {
-                        const int tA = lamD - Ad;
-                        const int BloA = max(0, tA - (dC - 1));
-                        dA_ = rd[lsD + rsT[lamD * dA + Ad] + (B - BloA)];
-                    }
-                    vA = !hUA ? dA_ : (!hDA ? uA : eik_min(uA, dA_));
-                }
+                const int A = Alo + (p >> sl);
+                const int B = ((p & smask) << 5) + lane;
+                const int C = lam - A - B;
+                if (B >= dB || (unsigned)C >= (unsigned)dC) continue;
+                const int ab = A * pg + B;
+                const int sab = A * pitch + B;
+                const double own = rd[base0 + ab];
+                // a missing neighbour (domain boundary) is +inf: min() then returns the existing one,
+                // which is the reference's mirror rule (Eikonal3D.cpp:47-52)
+                const bool hUA = (unsigned)(A - dir) < (unsigned)dA, hDA = (unsigned)(A + dir) < (unsigned)dA;
+                const bool hUB = (unsigned)(B - dir) < (unsigned)dB, hDB = (unsigned)(B + dir) < (unsigned)dB;
+                const bool hUC = (unsigned)(C - dir) < (unsigned)dC, hDC = (unsigned)(C + dir) < (unsigned)dC;
+                const int dn = baseD + ab;
+                double uA = EIK_INF, uB = EIK_INF, uC = EIK_INF, dA_ = EIK_INF, dB_ = EIK_INF, dC_ = EIK_INF;
+                if (hDA) dA_ = rd[dn + dpg];
+                if (hDB) dB_ = rd[dn + dir];
+                if (hDC) dC_ = rd[dn];
+                if (hUA) uA = shPrev[sab - dpitch];
+                if (hUB) uB = shPrev[sab - dir];
+                if (hUC) uC = shPrev[sab];
+                const double vA = eik_min(uA, dA_), vB = eik_min(uB, dB_), vC = eik_min(uC, dC_);
                 double res = own;
                 const double amin = eik_min(eik_min(vA, vB), vC);
                 if (amin < own) {
-                    const double fv = fl[off];
+                    const double fv = fl[base0 + ab];
                     const double un = eik_solve3_pre(vA, vB, vC, fv * h, fv * fv * h * h);
                     if (un < own) res = un;
                 }
-                shCur[A * pitch + B] = res;
+                shCur[sab] = res;
             }
         }
         __syncthreads();
-        // ------------------------------------------------------------------ phase 2
+        // ------------------------------------------------------------------ phase 2: write in X's layout
         {
             const int base = W.sh0 + W.shL * lam;
             const int lamX0 = W.lx0 + W.lxL * lam;
-            const int npairs = X.dA * segsX;
+            const int vlo = kappa > 0 ? max(0, -lamX0) : max(0, lamX0 - TX);
+            const int vhi = kappa > 0 ? min(X.dA - 1, TX - lamX0) : min(X.dA - 1, lamX0);
+            const int npairs = (vhi - vlo + 1) << slX;
             for (int p = warp; p < npairs; p += NW) {
-                const int v = p / segsX;
-                const int seg = p - v * segsX;
+                const int v = vlo + (p >> slX);
+                const int t = ((p & smaskX) << 5) + lane;
                 const int lamX = lamX0 + W.lxV * v;
-                if ((unsigned)lamX >= (unsigned)X.nlev) continue;
-                const int tX = lamX - v;
-                const int Blo = max(0, tX - (X.dC - 1)), Bhi = min(X.dB - 1, tX);
-                const int t = Blo + seg * 32 + lane;
-                if (t > Bhi) continue;
+                const int CX = lamX - v - t;
+                if (t >= X.dB || (unsigned)CX >= (unsigned)X.dC) continue;
                 const double val = shCur[base + W.shV * v + W.shT * t];
-                const int offX = lsX[lamX] + rsX[lamX * X.dA + v] + (t - Blo);
+                const int offX = (riX[lamX] + v - max(0, lamX - (X.dB - 1) - (X.dC - 1))) * X.pg + t;
                 wr[offX] = val;
                 if (cmp) {
                     const double dd = fabs(val - cmp[offX]);
@@ -128,7 +117,7 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
     __syncthreads();   // the next sweep reads what this one wrote to global memory
 }
 
-// bufs: S x 3 x N doubles; buffer 0 of every source holds u0 in layout L0 on entry.
+// bufs: S x 3 x Mmax doubles; buffer 0 of every source holds u0 in layout L0 on entry.
 // where[src] receives the index (0..2) of the buffer holding the result (layout L0).
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__restrict__ bufs,
@@ -139,7 +128,8 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
     extern __shared__ double sheets[];
     __shared__ double red[NT / 32];
     double *shA = sheets, *shB = sheets + P.sheet;
-    const long long N = P.N;
+    const long long N = P.Mmax;        // slots per buffer (padded rows)
+    const long long MF = P.Mmax;       // slots per f layout
     for (int src = blockIdx.x; src < S; src += gridDim.x) {
         double *B3 = bufs + (long long)src * 3 * N;
         int o = 0, a = 1, b = 2;
@@ -148,14 +138,14 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
         while (r < max_rounds) {
             double err = 0.0;
             double *Bo = B3 + o * N, *Ba = B3 + a * N, *Bb = B3 + b * N;
-            sweep3d_v1<NT>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * N, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * N, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * N, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * N, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * N, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * N, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * N, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * N, Bo, h, shA, shB, err);
+            sweep3d_v1<NT>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, err);
+            sweep3d_v1<NT>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, err);
+            sweep3d_v1<NT>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, err);
+            sweep3d_v1<NT>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, err);
+            sweep3d_v1<NT>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, err);
+            sweep3d_v1<NT>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, err);
+            sweep3d_v1<NT>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, err);
+            sweep3d_v1<NT>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, err);
             const double e = block_max<NT>(err, red);
             if (threadIdx.x == 0 && errs) errs[(long long)src * max_rounds + r] = e;
             r++;
@@ -183,7 +173,7 @@ __global__ void k_f_to_layouts(const Plan3 P, const double *__restrict__ f, doub
         const int k = id % l, t = id / l, j = t % n, i = t / n;
         const double v = f[id];
 #pragma unroll
-        for (int q = 0; q < NLAYOUT; q++) flay[(long long)q * P.N + lay_offset(P.lay[q], P.ext, i, j, k)] = v;
+        for (int q = 0; q < NLAYOUT; q++) flay[(long long)q * P.Mmax + lay_offset(P.lay[q], P.ext, i, j, k)] = v;
     }
 }
 
@@ -192,7 +182,7 @@ __global__ void k_u0_to_L0(const Plan3 P, const double *__restrict__ U0, double 
     const int n = P.ext[1], l = P.ext[2];
     const int src = blockIdx.y;
     const double *u0 = U0 + (long long)src * P.N;
-    double *b0 = bufs + (long long)src * 3 * P.N;
+    double *b0 = bufs + (long long)src * 3 * P.Mmax;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < P.N; id += gridDim.x * blockDim.x) {
         const int k = id % l, t = id / l, j = t % n, i = t / n;
         b0[lay_offset(P.lay[0], P.ext, i, j, k)] = u0[id];
@@ -204,7 +194,7 @@ __global__ void k_L0_to_rowmajor(const Plan3 P, const double *__restrict__ bufs,
                                  double *__restrict__ U) {
     const int n = P.ext[1], l = P.ext[2];
     const int src = blockIdx.y;
-    const double *b = bufs + ((long long)src * 3 + where[src]) * P.N;
+    const double *b = bufs + ((long long)src * 3 + where[src]) * P.Mmax;
     double *u = U + (long long)src * P.N;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < P.N; id += gridDim.x * blockDim.x) {
         const int k = id % l, t = id / l, j = t % n, i = t / n;

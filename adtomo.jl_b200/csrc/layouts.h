@@ -8,7 +8,9 @@
 // we therefore store a field LEVEL BY LEVEL: all nodes of level 0, then level 1, ...; inside a
 // level, rows of constant "major" coordinate A, and inside a row ascending "minor" coordinate B
 // (the third, "derived" coordinate is C = lambda - A - B).  A whole level is one contiguous block
-// and a sweep streams it exactly once.
+// and a sweep streams it exactly once.  Rows are padded to a fixed pitch (minor extent rounded up
+// to 4 doubles, so rows start sector-aligned and the offset of a node is a multiply-add: no per-row
+// table); the padding costs address space (<= 2x), not traffic.
 //
 // Consecutive sweeps of the reference's order differ in the sign of exactly ONE axis (Gray code),
 // and the intersection of a level of sweep P with a level of the next sweep X is a grid line with
@@ -33,8 +35,9 @@ struct LayoutDev {
     int dA, dB, dC;      // extents along major / minor / derived
     int nlev;            // dA+dB+dC-2
     int pitch;           // row pitch of the shared-memory sheet (>= dB, == 2 mod 4)
-    const int *levelStart;   // [nlev+1]   offset of a level in the field
-    const int *rowStart;     // [nlev*dA]  offset of row A inside its level
+    int pg;              // row pitch in global memory (dB rounded up to a multiple of 4)
+    int M;               // slots of one field in this layout = (number of rows) * pg  (>= N)
+    const int *rowIndex; // [nlev+1]   index of the first row of a level (rows of a level: A = Alo..Ahi)
 };
 
 struct SweepDev {
@@ -46,6 +49,7 @@ struct SweepDev {
 struct Plan3 {
     int ext[3];
     int N;
+    int Mmax;             // max over layouts of M: slots per field buffer
     int sheet;            // doubles per shared-memory sheet (max over layouts of dA*pitch)
     LayoutDev lay[NLAYOUT];
     SweepDev sw[8];
@@ -67,16 +71,16 @@ LAY_HD int lay_offset(const LayoutDev &L, const int *ext, int xi, int xj, int xk
     const int B = L.flip[L.ax1] ? ext[L.ax1] - 1 - x[L.ax1] : x[L.ax1];
     const int C = L.flip[L.ax2] ? ext[L.ax2] - 1 - x[L.ax2] : x[L.ax2];
     const int lam = A + B + C;
-    const int Blo = lay_imax(0, lam - A - (L.dC - 1));
-    return L.levelStart[lam] + L.rowStart[lam * L.dA + A] + (B - Blo);
+    const int Alo = lay_imax(0, lam - (L.dB - 1) - (L.dC - 1));
+    return (L.rowIndex[lam] + A - Alo) * L.pg + B;
 }
 
 // ---------------------------------------------------------------------------------------------
 // host-side construction
 // ---------------------------------------------------------------------------------------------
 struct HostLayout {
-    LayoutDev d;                  // levelStart/rowStart point into the vectors below
-    std::vector<int> levelStart, rowStart;
+    LayoutDev d;                  // rowIndex points into the vector below
+    std::vector<int> rowIndex;
 };
 
 inline void build_layout(HostLayout &H, const int ext[3], const int sign[3], int major) {
@@ -93,23 +97,17 @@ inline void build_layout(HostLayout &H, const int ext[3], const int sign[3], int
     int p = L.dB;
     while ((p & 3) != 2) p++;
     L.pitch = p;
-    H.levelStart.assign(L.nlev + 1, 0);
-    H.rowStart.assign((size_t)L.nlev * L.dA, 0);
+    L.pg = (L.dB + 3) & ~3;
+    H.rowIndex.assign(L.nlev + 1, 0);
     int acc = 0;
     for (int lam = 0; lam < L.nlev; lam++) {
-        H.levelStart[lam] = acc;
-        int racc = 0;
-        for (int A = 0; A < L.dA; A++) {
-            H.rowStart[(size_t)lam * L.dA + A] = racc;
-            int t = lam - A;
-            int lo = lay_imax(0, t - (L.dC - 1)), hi = lay_imin(L.dB - 1, t);
-            if (hi >= lo) racc += hi - lo + 1;
-        }
-        acc += racc;
+        H.rowIndex[lam] = acc;
+        const int Alo = lay_imax(0, lam - (L.dB - 1) - (L.dC - 1)), Ahi = lay_imin(L.dA - 1, lam);
+        acc += Ahi - Alo + 1;
     }
-    H.levelStart[L.nlev] = acc;
-    L.levelStart = H.levelStart.data();
-    L.rowStart = H.rowStart.data();
+    H.rowIndex[L.nlev] = acc;
+    L.M = acc * L.pg;
+    L.rowIndex = H.rowIndex.data();
 }
 
 struct HostPlan {
@@ -126,11 +124,13 @@ inline bool build_plan(HostPlan &HP, int m, int n, int l) {
     static const int signs[NLAYOUT][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, 1}};
     static const int majors[NLAYOUT] = {1, 0, 1, 0, 2};
     P.sheet = 0;
+    P.Mmax = 0;
     for (int q = 0; q < NLAYOUT; q++) {
         build_layout(HP.lay[q], P.ext, signs[q], majors[q]);
         P.lay[q] = HP.lay[q].d;
-        if (HP.lay[q].levelStart.back() != P.N) return false;
+        if (HP.lay[q].rowIndex.back() != P.lay[q].dA * (P.lay[q].dB + P.lay[q].dC - 1)) return false;
         P.sheet = lay_imax(P.sheet, P.lay[q].dA * P.lay[q].pitch);
+        P.Mmax = lay_imax(P.Mmax, P.lay[q].M);
     }
     static const int sched[8][3] = {{0, 1, 1}, {1, 2, 1}, {2, 3, 1}, {3, 4, 1}, {4, 2, -1}, {2, 3, -1}, {3, 0, -1}, {0, 0, -1}};
     // reference sweep directions, to double-check the schedule (Eikonal3D.cpp:59-68)

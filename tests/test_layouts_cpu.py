@@ -29,13 +29,13 @@ def emul():
 
 
 @pytest.mark.parametrize("dims", [(2, 2, 2), (5, 4, 3), (3, 9, 4), (8, 8, 8), (7, 3, 11), (16, 12, 6)])
-def test_layouts_are_permutations(emul, dims):
+def test_layouts_are_injective(emul, dims):
     m, n, l = dims
     N = m * n * l
     for q in range(5):
         out = np.empty(N, dtype=np.int32)
         assert emul.emul_layout_offsets(m, n, l, q, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == 0
-        assert sorted(out.tolist()) == list(range(N)), f"layout {q} is not a permutation"
+        assert len(set(out.tolist())) == N and out.min() >= 0, f"layout {q} is not injective"
 
 
 @pytest.mark.parametrize("dims,tol", [((2, 2, 2), 1e-9), ((5, 4, 3), 1e-9), ((3, 9, 4), 1e-6), ((9, 7, 6), 1e-6),
