@@ -254,7 +254,9 @@ static int get_plan(adtomo_ctx *c, int m, int n, int l, PlanCache **out) {
         o += H.rowIndex.size();
     }
     CK(cudaMemcpy(pc->d_tables, host.data(), sizeof(int) * total, cudaMemcpyHostToDevice));
-    pc->smem_bytes = sizeof(double) * 2 * (size_t)pc->dev.sheet;
+    int ris = 0;
+    for (int q = 0; q < NLAYOUT; q++) ris = std::max(ris, pc->dev.lay[q].nlev + 1);
+    pc->smem_bytes = sizeof(double) * 2 * (size_t)pc->dev.sheet + sizeof(int) * (size_t)NLAYOUT * ris;
     c->plans.push_back(pc);
     *out = pc;
     return 0;
@@ -266,7 +268,9 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
     PlanCache *pc = nullptr;
     int rc = get_plan(c, d.m, d.n, d.l, &pc);
     if (rc) return rc;
-    if (!c->force_v0 && pc->smem_bytes <= SMEM_MAX_DYN) {
+    bool fits = pc->smem_bytes <= SMEM_MAX_DYN;
+    for (int q = 0; q < NLAYOUT; q++) fits = fits && pc->dev.lay[q].dB <= 32 * (NT1 / 32);
+    if (!c->force_v0 && fits) {
         // level-major path: convert in, sweep, convert out
         double *bufs, *flay;
         int *where;

@@ -9,6 +9,9 @@
 //            value goes to the second sheet.
 //   phase 2: the level is written to global memory in the NEXT sweep's layout, row by row of that
 //            layout (contiguous, coalesced), reading the sheet through an affine index map.
+// (Round-1 revision: phase 2 is gone -- each thread stores its result directly at the node's position
+// in the next sweep's layout; the 4 doubles of a sector are written within the same level step, so
+// L2 merges them and DRAM traffic stays 8 B/node.)
 // One __syncthreads per level.  The update is eik_solve3_pre (bit-exact with the reference) and is
 // skipped when no neighbour is smaller than the node (then the candidate cannot win the min).
 // Three rotating global buffers per source hold: the field at round start (for the L-inf stopping
@@ -21,10 +24,14 @@ namespace adtomo {
 
 #define EIK_INF __longlong_as_double(0x7ff0000000000000LL)
 
+// One directional sweep.  shA/shB: two (dA+2) x pitch sheets with a +inf border (a missing upwind
+// neighbour then reads +inf and min() returns the existing one: the reference's mirror rule,
+// Eikonal3D.cpp:47-52).  ri: shared-memory copy of the layouts' rowIndex tables, stride riStride.
 template <int NT>
 __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const double *rd, double *wr,
                                            const double *__restrict__ fl, const double *cmp, const double h,
-                                           double *shA, double *shB, double &err) {
+                                           double *shA, double *shB, const int *ri, const int riStride,
+                                           double &err) {
     const SweepDev W = P.sw[sw];
     const LayoutDev &L = P.lay[W.rl];
     const LayoutDev &X = P.lay[W.wl];
@@ -32,49 +39,53 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = NT / 32;
     const int dA = L.dA, dB = L.dB, dC = L.dC, pitch = L.pitch, pg = L.pg, nlev = L.nlev;
-    // segments of 32 minor coordinates per row, rounded up to a power of two (shift/mask, no division)
+    const int *riL = ri + W.rl * riStride;
+    const int *riX = ri + W.wl * riStride;
+    // a warp owns one 32-wide segment of minor coordinates (B is loop invariant) and strides over rows
     int sl = 0;
     while ((32 << sl) < dB) sl++;
-    const int smask = (1 << sl) - 1;
-    int slX = 0;
-    while ((32 << slX) < X.dB) slX++;
-    const int smaskX = (1 << slX) - 1;
-    const int TX = X.dB + X.dC - 2;
-    const int kappa = W.lxV - 1;   // tX = lamX0 + kappa*v, kappa = +-1
-    const int *__restrict__ riL = L.rowIndex;
-    const int *__restrict__ riX = X.rowIndex;
+    const int B = ((warp & ((1 << sl) - 1)) << 5) + lane;
+    const int row0 = warp >> sl, rowStep = NW >> sl;
+    const bool activeB = B < dB;
+    const bool hDB = (unsigned)(B + dir) < (unsigned)dB;
     const int dpg = dir * pg, dpitch = dir * pitch;
+    const int TXc = (X.dB - 1) + (X.dC - 1);
+    const int pgX = X.pg;
+    // +inf borders for this layout's sheet geometry
+    for (int q = threadIdx.x; q < pitch; q += NT) {
+        shA[q] = EIK_INF; shB[q] = EIK_INF;
+        shA[(dA + 1) * pitch + q] = EIK_INF; shB[(dA + 1) * pitch + q] = EIK_INF;
+    }
+    for (int q = threadIdx.x; q < dA + 2; q += NT) {
+        shA[q * pitch] = EIK_INF; shB[q * pitch] = EIK_INF;
+        shA[q * pitch + dB + 1] = EIK_INF; shB[q * pitch + dB + 1] = EIK_INF;
+    }
+    __syncthreads();
     double *shPrev = shA, *shCur = shB;
     for (int step = 0; step < nlev; step++) {
         const int lam = dir > 0 ? step : nlev - 1 - step;
-        // ------------------------------------------------------------------ phase 1: update the level
-        {
-            const int Alo = max(0, lam - (dB - 1) - (dC - 1)), Ahi = min(dA - 1, lam);
-            const int npairs = (Ahi - Alo + 1) << sl;
-            const int lamD = lam + dir;
-            const bool hasD = (unsigned)lamD < (unsigned)nlev;
-            const int base0 = (riL[lam] - Alo) * pg;
-            const int baseD = hasD ? (riL[lamD] - max(0, lamD - (dB - 1) - (dC - 1))) * pg : 0;
-            for (int p = warp; p < npairs; p += NW) {
-                const int A = Alo + (p >> sl);
-                const int B = ((p & smask) << 5) + lane;
+        const int Alo = max(0, lam - (dB - 1) - (dC - 1)), Ahi = min(dA - 1, lam);
+        const int lamD = lam + dir;
+        const bool hasD = (unsigned)lamD < (unsigned)nlev;
+        const int base0 = (riL[lam] - Alo) * pg + B;
+        const int baseD = hasD ? (riL[lamD] - max(0, lamD - (dB - 1) - (dC - 1))) * pg + B : 0;
+        const int lamX0 = W.lx0 + W.lxL * lam;
+        if (activeB) {
+            for (int A = Alo + row0; A <= Ahi; A += rowStep) {
                 const int C = lam - A - B;
-                if (B >= dB || (unsigned)C >= (unsigned)dC) continue;
-                const int ab = A * pg + B;
-                const int sab = A * pitch + B;
+                if ((unsigned)C >= (unsigned)dC) continue;
+                const int ab = A * pg;
+                const int sab = (A + 1) * pitch + B + 1;
                 const double own = rd[base0 + ab];
-                // a missing neighbour (domain boundary) is +inf: min() then returns the existing one,
-                // which is the reference's mirror rule (Eikonal3D.cpp:47-52)
-                const bool hUA = (unsigned)(A - dir) < (unsigned)dA, hDA = (unsigned)(A + dir) < (unsigned)dA;
-                const bool hUB = (unsigned)(B - dir) < (unsigned)dB, hDB = (unsigned)(B + dir) < (unsigned)dB;
+                const bool hDA = (unsigned)(A + dir) < (unsigned)dA;
                 const bool hUC = (unsigned)(C - dir) < (unsigned)dC, hDC = (unsigned)(C + dir) < (unsigned)dC;
                 const int dn = baseD + ab;
-                double uA = EIK_INF, uB = EIK_INF, uC = EIK_INF, dA_ = EIK_INF, dB_ = EIK_INF, dC_ = EIK_INF;
+                double uC = EIK_INF, dA_ = EIK_INF, dB_ = EIK_INF, dC_ = EIK_INF;
                 if (hDA) dA_ = rd[dn + dpg];
                 if (hDB) dB_ = rd[dn + dir];
                 if (hDC) dC_ = rd[dn];
-                if (hUA) uA = shPrev[sab - dpitch];
-                if (hUB) uB = shPrev[sab - dir];
+                const double uA = shPrev[sab - dpitch];
+                const double uB = shPrev[sab - dir];
                 if (hUC) uC = shPrev[sab];
                 const double vA = eik_min(uA, dA_), vB = eik_min(uB, dB_), vC = eik_min(uC, dC_);
                 double res = own;
@@ -85,36 +96,24 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
                     if (un < own) res = un;
                 }
                 shCur[sab] = res;
-            }
-        }
-        __syncthreads();
-        // ------------------------------------------------------------------ phase 2: write in X's layout
-        {
-            const int base = W.sh0 + W.shL * lam;
-            const int lamX0 = W.lx0 + W.lxL * lam;
-            const int vlo = kappa > 0 ? max(0, -lamX0) : max(0, lamX0 - TX);
-            const int vhi = kappa > 0 ? min(X.dA - 1, TX - lamX0) : min(X.dA - 1, lamX0);
-            const int npairs = (vhi - vlo + 1) << slX;
-            for (int p = warp; p < npairs; p += NW) {
-                const int v = vlo + (p >> slX);
-                const int t = ((p & smaskX) << 5) + lane;
+                // position in the next sweep's layout
+                const int cv = W.vi == 0 ? A : (W.vi == 1 ? B : C);
+                const int ct = W.ti == 0 ? A : (W.ti == 1 ? B : C);
+                const int v = W.vs * cv + W.vo, t = W.ts * ct + W.to;
                 const int lamX = lamX0 + W.lxV * v;
-                const int CX = lamX - v - t;
-                if (t >= X.dB || (unsigned)CX >= (unsigned)X.dC) continue;
-                const double val = shCur[base + W.shV * v + W.shT * t];
-                const int offX = (riX[lamX] + v - max(0, lamX - (X.dB - 1) - (X.dC - 1))) * X.pg + t;
-                wr[offX] = val;
+                const int offX = (riX[lamX] + v - max(0, lamX - TXc)) * pgX + t;
+                wr[offX] = res;
                 if (cmp) {
-                    const double dd = fabs(val - cmp[offX]);
+                    const double dd = fabs(res - cmp[offX]);
                     err = (err < dd) ? dd : err;
                 }
             }
         }
+        __syncthreads();
         double *tmp = shPrev;
         shPrev = shCur;
         shCur = tmp;
     }
-    __syncthreads();   // the next sweep reads what this one wrote to global memory
 }
 
 // bufs: S x 3 x Mmax doubles; buffer 0 of every source holds u0 in layout L0 on entry.
@@ -128,6 +127,12 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
     extern __shared__ double sheets[];
     __shared__ double red[NT / 32];
     double *shA = sheets, *shB = sheets + P.sheet;
+    int *ri = (int *)(sheets + 2 * (size_t)P.sheet);
+    int riStride = 0;
+    for (int q = 0; q < NLAYOUT; q++) riStride = max(riStride, P.lay[q].nlev + 1);
+    for (int q = 0; q < NLAYOUT; q++)
+        for (int t = threadIdx.x; t <= P.lay[q].nlev; t += NT) ri[q * riStride + t] = P.lay[q].rowIndex[t];
+    __syncthreads();
     const long long N = P.Mmax;        // slots per buffer (padded rows)
     const long long MF = P.Mmax;       // slots per f layout
     for (int src = blockIdx.x; src < S; src += gridDim.x) {
@@ -138,14 +143,14 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
         while (r < max_rounds) {
             double err = 0.0;
             double *Bo = B3 + o * N, *Ba = B3 + a * N, *Bb = B3 + b * N;
-            sweep3d_v1<NT>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, err);
-            sweep3d_v1<NT>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, err);
+            sweep3d_v1<NT>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, ri, riStride, err);
             const double e = block_max<NT>(err, red);
             if (threadIdx.x == 0 && errs) errs[(long long)src * max_rounds + r] = e;
             r++;

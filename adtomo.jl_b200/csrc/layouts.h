@@ -34,23 +34,25 @@ struct LayoutDev {
     int flip[3];         // per PHYSICAL axis: canonical coordinate = ext-1-x when 1
     int dA, dB, dC;      // extents along major / minor / derived
     int nlev;            // dA+dB+dC-2
-    int pitch;           // row pitch of the shared-memory sheet (>= dB, == 2 mod 4)
+    int pitch;           // row pitch of the shared-memory sheet; the sheet is (dA+2) x pitch with a +inf border
     int pg;              // row pitch in global memory (dB rounded up to a multiple of 4)
     int M;               // slots of one field in this layout = (number of rows) * pg  (>= N)
     const int *rowIndex; // [nlev+1]   index of the first row of a level (rows of a level: A = Alo..Ahi)
 };
 
 struct SweepDev {
-    int rl, wl, dir;          // layout read, layout written, +1 ascending / -1 descending levels
-    int sh0, shL, shV, shT;   // write phase: sheet address of X-row v, X-minor t:  sh0+shL*lam+shV*v+shT*t
-    int lx0, lxL, lxV;        // write phase: X level  lamX = lx0 + lxL*lam + lxV*v
+    int rl, wl, dir;          // layout read (R), layout written (X), +1 ascending / -1 descending levels
+    // position of an R node (A,B,C) in X:  v = vs*coord[vi]+vo (X major), t = ts*coord[ti]+to (X minor),
+    // coord = {A,B,C}; X level lamX = lx0 + lxL*lam + lxV*v
+    int vi, vs, vo, ti, ts, to;
+    int lx0, lxL, lxV;
 };
 
 struct Plan3 {
     int ext[3];
     int N;
     int Mmax;             // max over layouts of M: slots per field buffer
-    int sheet;            // doubles per shared-memory sheet (max over layouts of dA*pitch)
+    int sheet;            // doubles per shared-memory sheet (max over layouts of (dA+2)*pitch)
     LayoutDev lay[NLAYOUT];
     SweepDev sw[8];
 };
@@ -94,7 +96,7 @@ inline void build_layout(HostLayout &H, const int ext[3], const int sign[3], int
     for (int a = 0; a < 3; a++) L.flip[a] = sign[a] < 0;
     L.dA = ext[major]; L.dB = ext[minor]; L.dC = ext[derived];
     L.nlev = L.dA + L.dB + L.dC - 2;
-    int p = L.dB;
+    int p = L.dB + 2;            // one +inf border column on each side
     while ((p & 3) != 2) p++;
     L.pitch = p;
     L.pg = (L.dB + 3) & ~3;
@@ -129,7 +131,7 @@ inline bool build_plan(HostPlan &HP, int m, int n, int l) {
         build_layout(HP.lay[q], P.ext, signs[q], majors[q]);
         P.lay[q] = HP.lay[q].d;
         if (HP.lay[q].rowIndex.back() != P.lay[q].dA * (P.lay[q].dB + P.lay[q].dC - 1)) return false;
-        P.sheet = lay_imax(P.sheet, P.lay[q].dA * P.lay[q].pitch);
+        P.sheet = lay_imax(P.sheet, (P.lay[q].dA + 2) * P.lay[q].pitch);
         P.Mmax = lay_imax(P.Mmax, P.lay[q].M);
     }
     static const int sched[8][3] = {{0, 1, 1}, {1, 2, 1}, {2, 3, 1}, {3, 4, 1}, {4, 2, -1}, {2, 3, -1}, {3, 0, -1}, {0, 0, -1}};
@@ -153,19 +155,23 @@ inline bool build_plan(HostPlan &HP, int m, int n, int l) {
         W.lxL = sigma;
         W.lxV = 1 - sigma * sg[X.ax0];
         W.lx0 = -sigma * O;
-        auto addr = [&](int lam, int v, int t) {
-            int lamX = W.lx0 + W.lxL * lam + W.lxV * v;
-            int cX[3];
-            cX[X.ax0] = v; cX[X.ax1] = t; cX[X.ax2] = lamX - v - t;
+        auto which = [&](int axis) { return axis == R.ax0 ? 0 : (axis == R.ax1 ? 1 : 2); };
+        W.vi = which(X.ax0); W.vs = sg[X.ax0]; W.vo = of[X.ax0];
+        W.ti = which(X.ax1); W.ts = sg[X.ax1]; W.to = of[X.ax1];
+        // brute-force check of the map on the corners and a few interior nodes
+        for (int probe = 0; probe < 27; probe++) {
+            int x[3];
+            int q = probe;
+            for (int a2 = 0; a2 < 3; a2++) { int r = q % 3; q /= 3; x[a2] = r == 0 ? 0 : (r == 1 ? P.ext[a2] / 2 : P.ext[a2] - 1); }
             int cR[3];
-            for (int a = 0; a < 3; a++) cR[a] = sg[a] * cX[a] + of[a];
-            return cR[R.ax0] * R.pitch + cR[R.ax1];
-        };
-        W.sh0 = addr(0, 0, 0);
-        W.shL = addr(1, 0, 0) - W.sh0;
-        W.shV = addr(0, 1, 0) - W.sh0;
-        W.shT = addr(0, 0, 1) - W.sh0;
-        if (addr(3, 5, 7) != W.sh0 + 3 * W.shL + 5 * W.shV + 7 * W.shT) return false;
+            for (int a2 = 0; a2 < 3; a2++) cR[a2] = R.flip[a2] ? P.ext[a2] - 1 - x[a2] : x[a2];
+            const int coord[3] = {cR[R.ax0], cR[R.ax1], cR[R.ax2]};
+            const int lam = coord[0] + coord[1] + coord[2];
+            const int v = W.vs * coord[W.vi] + W.vo, t = W.ts * coord[W.ti] + W.to;
+            const int lamX = W.lx0 + W.lxL * lam + W.lxV * v;
+            const int off = (X.rowIndex[lamX] + v - lay_imax(0, lamX - (X.dB - 1) - (X.dC - 1))) * X.pg + t;
+            if (off != lay_offset(X, P.ext, x[0], x[1], x[2])) return false;
+        }
     }
     HP.ok = true;
     return true;

@@ -20,32 +20,33 @@ static void sweep(const Plan3 &P, int sw, const double *rd, double *wr, const do
     const LayoutDev &L = P.lay[W.rl];
     const LayoutDev &X = P.lay[W.wl];
     const int dir = W.dir, dA = L.dA, dB = L.dB, dC = L.dC, pitch = L.pitch, pg = L.pg, nlev = L.nlev;
-    const int TX = X.dB + X.dC - 2, kappa = W.lxV - 1;
     const int dpg = dir * pg, dpitch = dir * pitch;
+    const int TXc = (X.dB - 1) + (X.dC - 1);
+    for (int q = 0; q < pitch; q++) { shA[q] = shB[q] = INF; shA[(dA + 1) * pitch + q] = shB[(dA + 1) * pitch + q] = INF; }
+    for (int q = 0; q < dA + 2; q++) { shA[q * pitch] = shB[q * pitch] = INF; shA[q * pitch + dB + 1] = shB[q * pitch + dB + 1] = INF; }
     double *shPrev = shA, *shCur = shB;
     for (int step = 0; step < nlev; step++) {
         const int lam = dir > 0 ? step : nlev - 1 - step;
         const int Alo = std::max(0, lam - (dB - 1) - (dC - 1)), Ahi = std::min(dA - 1, lam);
         const int lamD = lam + dir;
         const bool hasD = lamD >= 0 && lamD < nlev;
-        const int base0 = (L.rowIndex[lam] - Alo) * pg;
-        const int baseD = hasD ? (L.rowIndex[lamD] - std::max(0, lamD - (dB - 1) - (dC - 1))) * pg : 0;
+        const int lamX0 = W.lx0 + W.lxL * lam;
         for (int A = Alo; A <= Ahi; A++)
             for (int B = 0; B < dB; B++) {
                 const int C = lam - A - B;
                 if (C < 0 || C >= dC) continue;
-                const int ab = A * pg + B, sab = A * pitch + B;
+                const int base0 = (L.rowIndex[lam] - Alo) * pg + B;
+                const int baseD = hasD ? (L.rowIndex[lamD] - std::max(0, lamD - (dB - 1) - (dC - 1))) * pg + B : 0;
+                const int ab = A * pg, sab = (A + 1) * pitch + B + 1;
                 const double own = rd[base0 + ab];
-                const bool hUA = A - dir >= 0 && A - dir < dA, hDA = A + dir >= 0 && A + dir < dA;
-                const bool hUB = B - dir >= 0 && B - dir < dB, hDB = B + dir >= 0 && B + dir < dB;
+                const bool hDA = A + dir >= 0 && A + dir < dA, hDB = B + dir >= 0 && B + dir < dB;
                 const bool hUC = C - dir >= 0 && C - dir < dC, hDC = C + dir >= 0 && C + dir < dC;
                 const int dn = baseD + ab;
-                double uA = INF, uB = INF, uC = INF, dA_ = INF, dB_ = INF, dC_ = INF;
+                double uC = INF, dA_ = INF, dB_ = INF, dC_ = INF;
                 if (hDA) dA_ = rd[dn + dpg];
                 if (hDB) dB_ = rd[dn + dir];
                 if (hDC) dC_ = rd[dn];
-                if (hUA) uA = shPrev[sab - dpitch];
-                if (hUB) uB = shPrev[sab - dir];
+                const double uA = shPrev[sab - dpitch], uB = shPrev[sab - dir];
                 if (hUC) uC = shPrev[sab];
                 const double vA = eik_min(uA, dA_), vB = eik_min(uB, dB_), vC = eik_min(uC, dC_);
                 double res = own;
@@ -56,23 +57,13 @@ static void sweep(const Plan3 &P, int sw, const double *rd, double *wr, const do
                     if (un < own) res = un;
                 }
                 shCur[sab] = res;
-            }
-        const int base = W.sh0 + W.shL * lam, lamX0 = W.lx0 + W.lxL * lam;
-        const int vlo = kappa > 0 ? std::max(0, -lamX0) : std::max(0, lamX0 - TX);
-        const int vhi = kappa > 0 ? std::min(X.dA - 1, TX - lamX0) : std::min(X.dA - 1, lamX0);
-        int written = 0;
-        for (int v = vlo; v <= vhi; v++)
-            for (int t = 0; t < X.dB; t++) {
+                const int cv = W.vi == 0 ? A : (W.vi == 1 ? B : C), ct = W.ti == 0 ? A : (W.ti == 1 ? B : C);
+                const int v = W.vs * cv + W.vo, t = W.ts * ct + W.to;
                 const int lamX = lamX0 + W.lxV * v;
-                const int CX = lamX - v - t;
-                if (CX < 0 || CX >= X.dC) continue;
-                const double val = shCur[base + W.shV * v + W.shT * t];
-                const int offX = (X.rowIndex[lamX] + v - std::max(0, lamX - (X.dB - 1) - (X.dC - 1))) * X.pg + t;
-                wr[offX] = val;
-                written++;
-                if (cmp) err = std::max(err, std::fabs(val - cmp[offX]));
+                const int offX = (X.rowIndex[lamX] + v - std::max(0, lamX - TXc)) * X.pg + t;
+                wr[offX] = res;
+                if (cmp) err = std::max(err, std::fabs(res - cmp[offX]));
             }
-        (void)written;
         std::swap(shPrev, shCur);
     }
 }
