@@ -50,6 +50,7 @@ struct adtomo_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     std::vector<std::pair<int, int>> ev_used;   // (phase, pool index)
     std::vector<struct PlanCache *> plans;      // level-major layout plans, one per grid shape
+    int fwd_variant = 0;                        // tuning aid: ADTOMO_FWD_VARIANT selects <threads, nodes per lane>
     int force_v0 = 0;                           // debugging aid: ADTOMO_FORCE_V0=1 selects the row-major kernel
 };
 
@@ -132,6 +133,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     CK(cudaEventCreate(&c->ev1));
     const char *fv0 = getenv("ADTOMO_FORCE_V0");
     c->force_v0 = (fv0 && fv0[0] == '1');
+    const char *fvv = getenv("ADTOMO_FWD_VARIANT");
+    c->fwd_variant = fvv ? atoi(fvv) : 1;
     *out = c;
     return 0;
 }
@@ -256,7 +259,13 @@ static int get_plan(adtomo_ctx *c, int m, int n, int l, PlanCache **out) {
     CK(cudaMemcpy(pc->d_tables, host.data(), sizeof(int) * total, cudaMemcpyHostToDevice));
     int ris = 0;
     for (int q = 0; q < NLAYOUT; q++) ris = std::max(ris, pc->dev.lay[q].nlev + 1);
-    pc->smem_bytes = sizeof(double) * 2 * (size_t)pc->dev.sheet + sizeof(int) * (size_t)NLAYOUT * ris;
+    size_t prog = 0;
+    for (int q = 0; q < NLAYOUT; q++) {
+        int sl = 0;
+        while ((32 << sl) < pc->dev.lay[q].dB) sl++;
+        prog = std::max(prog, ((size_t)(pc->dev.lay[q].dA + 2) << sl) + 1);
+    }
+    pc->smem_bytes = sizeof(double) * 2 * (size_t)pc->dev.sheet + sizeof(int) * ((size_t)NLAYOUT * ris + prog + 8);
     c->plans.push_back(pc);
     *out = pc;
     return 0;
@@ -269,7 +278,7 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
     int rc = get_plan(c, d.m, d.n, d.l, &pc);
     if (rc) return rc;
     bool fits = pc->smem_bytes <= SMEM_MAX_DYN;
-    for (int q = 0; q < NLAYOUT; q++) fits = fits && pc->dev.lay[q].dB <= 32 * (NT1 / 32);
+    for (int q = 0; q < NLAYOUT; q++) fits = fits && pc->dev.lay[q].dB <= 256;   // at most 8 segments per row (wait loop uses 3*nseg lanes)
     if (!c->force_v0 && fits) {
         // level-major path: convert in, sweep, convert out
         double *bufs, *flay;
@@ -279,7 +288,10 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         WS(c, "fwd_where", int, S, where);
         static bool attr_set = false;
         if (!attr_set) {
-            CK(cudaFuncSetAttribute(k_fwd3d_v1<NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
+            CK(cudaFuncSetAttribute(k_fwd3d_v1<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
+            CK(cudaFuncSetAttribute(k_fwd3d_v1<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
+            CK(cudaFuncSetAttribute(k_fwd3d_v1<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
+            CK(cudaFuncSetAttribute(k_fwd3d_v1<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
             attr_set = true;
         }
         int pk = phase_begin(c, PH_CONVERT);
@@ -291,8 +303,12 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         LAUNCHED(c, "k_u0_to_L0");
         int grid = std::min(S, c->num_sms);
         pk = phase_begin(c, PH_FWD);
-        k_fwd3d_v1<NT1><<<grid, NT1, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds,
-                                                                 d_errs, where);
+        switch (c->fwd_variant) {
+            case 1: k_fwd3d_v1<1024, 2><<<grid, 1024, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where); break;
+            case 2: k_fwd3d_v1<512, 2><<<grid, 512, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where); break;
+            case 3: k_fwd3d_v1<512, 1><<<grid, 512, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where); break;
+            default: k_fwd3d_v1<1024, 1><<<grid, 1024, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where); break;
+        }
         phase_end(c, pk);
         LAUNCHED(c, "k_fwd3d_v1");
         pk = phase_begin(c, PH_CONVERT);
@@ -328,10 +344,10 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
     WS(c, "adj_counters", int, 3 * (size_t)S, cnts);
     CK(cudaMemsetAsync(cnts, 0, sizeof(int) * 3 * S, c->stream));
     int pk = phase_begin(c, PH_ADJ_SETUP);
-    k_adj3d_setup<<<elem_grid(c, d.N * S), 256, 0, c->stream>>>(dU, dU0, dG, X, dGU0, code, cnts, d, S);
+    k_adj3d_setup<<<dim3(std::min(elem_grid(c, d.N), 128), S), 256, 0, c->stream>>>(dU, dU0, dG, X, dGU0, code, cnts, d, S);
     LAUNCHED(c, "k_adj3d_setup");
     if (dGF || dGFsum) {
-        k_adj3d_count<<<elem_grid(c, d.N * S), 256, 0, c->stream>>>(code, cnt, Q, cnts + S, d, S);
+        k_adj3d_count<<<dim3(std::min(elem_grid(c, d.N), 128), S), 256, 0, c->stream>>>(code, cnt, Q, cnts + S, d, S);
         phase_end(c, pk);
         LAUNCHED(c, "k_adj3d_count");
         int occ = 1;

@@ -18,29 +18,28 @@ namespace adtomo {
 __global__ void k_adj3d_count(const unsigned char *__restrict__ code, unsigned char *__restrict__ cnt,
                               int *__restrict__ Q, int *__restrict__ qtail,
                               const Dims3 d, const int S) {
-    const long long total = d.N * S;
-    const long long si = (long long)d.n * d.l;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total;
-         q += (long long)gridDim.x * blockDim.x) {
-        const unsigned cd = code[q];
-        if (cd & ADJ_PIN) { cnt[q] = 0xFF; continue; }
-        const int src = (int)(q / d.N);
-        const long long id = q - (long long)src * d.N;
-        const int k = (int)(id % d.l);
-        const long long t = id / d.l;
-        const int j = (int)(t % d.n);
-        const int i = (int)(t / d.n);
+    const int src = blockIdx.y;
+    const long long base = (long long)src * d.N;
+    const unsigned char *cd_ = code + base;
+    const int N = (int)d.N, n = d.n, l = d.l, nl = d.n * d.l;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < N; id += gridDim.x * blockDim.x) {
+        const unsigned cd = cd_[id];
+        if (cd & ADJ_PIN) { cnt[base + id] = 0xFF; continue; }
+        const int i = id / nl;
+        const int r = id - i * nl;
+        const int j = r / l;
+        const int k = r - j * l;
         int c = 0;
-        if (i > 0 && ((code[q - si] >> 0) & 3u) == 2u) c++;
-        if (i < d.m - 1 && ((code[q + si] >> 0) & 3u) == 1u) c++;
-        if (j > 0 && ((code[q - d.l] >> 2) & 3u) == 2u) c++;
-        if (j < d.n - 1 && ((code[q + d.l] >> 2) & 3u) == 1u) c++;
-        if (k > 0 && ((code[q - 1] >> 4) & 3u) == 2u) c++;
-        if (k < d.l - 1 && ((code[q + 1] >> 4) & 3u) == 1u) c++;
-        cnt[q] = (unsigned char)c;
+        if (i > 0 && ((cd_[id - nl] >> 0) & 3u) == 2u) c++;
+        if (i < d.m - 1 && ((cd_[id + nl] >> 0) & 3u) == 1u) c++;
+        if (j > 0 && ((cd_[id - l] >> 2) & 3u) == 2u) c++;
+        if (j < n - 1 && ((cd_[id + l] >> 2) & 3u) == 1u) c++;
+        if (k > 0 && ((cd_[id - 1] >> 4) & 3u) == 2u) c++;
+        if (k < l - 1 && ((cd_[id + 1] >> 4) & 3u) == 1u) c++;
+        cnt[base + id] = (unsigned char)c;
         if (c == 0) {
             const int pos = atomicAdd(&qtail[src], 1);
-            Q[(long long)src * d.N + pos] = (int)id;
+            Q[base + pos] = id;
         }
     }
 }

@@ -27,7 +27,10 @@ namespace adtomo {
 // One directional sweep.  shA/shB: two (dA+2) x pitch sheets with a +inf border (a missing upwind
 // neighbour then reads +inf and min() returns the existing one: the reference's mirror rule,
 // Eikonal3D.cpp:47-52).  ri: shared-memory copy of the layouts' rowIndex tables, stride riStride.
-template <int NT>
+// NPL = nodes per lane and work item: a warp handles a 32*NPL-wide piece of a row, lane l owning the
+// minor coordinates B0+l, B0+l+32, ...; the NPL updates are independent and interleave (ILP), and the
+// per-item index arithmetic is amortised over NPL nodes.
+template <int NT, int NPL>
 __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const double *rd, double *wr,
                                            const double *__restrict__ fl, const double *cmp, const double h,
                                            double *shA, double *shB, const int *ri, const int riStride,
@@ -39,15 +42,14 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = NT / 32;
     const int dA = L.dA, dB = L.dB, dC = L.dC, pitch = L.pitch, pg = L.pg, nlev = L.nlev;
+    const int T = dB + dC - 2;
     const int *riL = ri + W.rl * riStride;
     const int *riX = ri + W.wl * riStride;
-    // a warp owns one 32-wide segment of minor coordinates (B is loop invariant) and strides over rows
+    // a warp owns one (32*NPL)-wide segment of minor coordinates (loop invariant) and strides over rows
     int sl = 0;
-    while ((32 << sl) < dB) sl++;
-    const int B = ((warp & ((1 << sl) - 1)) << 5) + lane;
+    while (((32 * NPL) << sl) < dB) sl++;
+    const int B0 = ((warp & ((1 << sl) - 1)) * (32 * NPL)) + lane;
     const int row0 = warp >> sl, rowStep = NW >> sl;
-    const bool activeB = B < dB;
-    const bool hDB = (unsigned)(B + dir) < (unsigned)dB;
     const int dpg = dir * pg, dpitch = dir * pitch;
     const int TXc = (X.dB - 1) + (X.dC - 1);
     const int pgX = X.pg;
@@ -64,48 +66,75 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
     double *shPrev = shA, *shCur = shB;
     for (int step = 0; step < nlev; step++) {
         const int lam = dir > 0 ? step : nlev - 1 - step;
-        const int Alo = max(0, lam - (dB - 1) - (dC - 1)), Ahi = min(dA - 1, lam);
+        const int Alo = max(0, lam - T), Ahi = min(dA - 1, lam);
         const int lamD = lam + dir;
         const bool hasD = (unsigned)lamD < (unsigned)nlev;
-        const int base0 = (riL[lam] - Alo) * pg + B;
-        const int baseD = hasD ? (riL[lamD] - max(0, lamD - (dB - 1) - (dC - 1))) * pg + B : 0;
+        const int base0 = (riL[lam] - Alo) * pg + B0;
+        const int baseD = hasD ? (riL[lamD] - max(0, lamD - T)) * pg + B0 : 0;
+        const int lamP = lam + 2 * dir;
+        const bool hasP = (unsigned)lamP < (unsigned)nlev;
+        const int baseP = hasP ? (riL[lamP] - max(0, lamP - T)) * pg + B0 : 0;
         const int lamX0 = W.lx0 + W.lxL * lam;
-        if (activeB) {
-            for (int A = Alo + row0; A <= Ahi; A += rowStep) {
-                const int C = lam - A - B;
-                if ((unsigned)C >= (unsigned)dC) continue;
-                const int ab = A * pg;
-                const int sab = (A + 1) * pitch + B + 1;
-                const double own = rd[base0 + ab];
-                const bool hDA = (unsigned)(A + dir) < (unsigned)dA;
-                const bool hUC = (unsigned)(C - dir) < (unsigned)dC, hDC = (unsigned)(C + dir) < (unsigned)dC;
-                const int dn = baseD + ab;
-                double uC = EIK_INF, dA_ = EIK_INF, dB_ = EIK_INF, dC_ = EIK_INF;
-                if (hDA) dA_ = rd[dn + dpg];
-                if (hDB) dB_ = rd[dn + dir];
-                if (hDC) dC_ = rd[dn];
-                const double uA = shPrev[sab - dpitch];
-                const double uB = shPrev[sab - dir];
-                if (hUC) uC = shPrev[sab];
-                const double vA = eik_min(uA, dA_), vB = eik_min(uB, dB_), vC = eik_min(uC, dC_);
-                double res = own;
-                const double amin = eik_min(eik_min(vA, vB), vC);
-                if (amin < own) {
-                    const double fv = fl[base0 + ab];
-                    const double un = eik_solve3_pre(vA, vB, vC, fv * h, fv * fv * h * h);
-                    if (un < own) res = un;
+        for (int A = Alo + row0; A <= Ahi; A += rowStep) {
+            const int ab = A * pg;
+            const int sab = (A + 1) * pitch + B0 + 1;
+            const int C0 = lam - A - B0;
+            const bool hDA = (unsigned)(A + dir) < (unsigned)dA;
+            bool valid[NPL];
+            double own[NPL], fv[NPL], dA_[NPL], dB_[NPL], dC_[NPL];
+#pragma unroll
+            for (int k = 0; k < NPL; k++) {
+                const int B = B0 + 32 * k, C = C0 - 32 * k;
+                valid[k] = (B < dB) && ((unsigned)C < (unsigned)dC);
+                own[k] = 0.0; fv[k] = 0.0; dA_[k] = EIK_INF; dB_[k] = EIK_INF; dC_[k] = EIK_INF;
+                if (valid[k]) {
+                    own[k] = rd[base0 + ab + 32 * k];
+                    fv[k] = fl[base0 + ab + 32 * k];
+                    const int dn = baseD + ab + 32 * k;
+                    if (hDA) dA_[k] = rd[dn + dpg];
+                    if ((unsigned)(B + dir) < (unsigned)dB) dB_[k] = rd[dn + dir];
+                    if ((unsigned)(C + dir) < (unsigned)dC) dC_[k] = rd[dn];
+                    // pull the level after next towards L1 (first used as downwind data of the next step)
+                    if (hasP && (unsigned)(C + 2 * dir) < (unsigned)dC) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(rd + baseP + ab + 32 * k));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fl + dn));
+                    }
                 }
-                shCur[sab] = res;
-                // position in the next sweep's layout
-                const int cv = W.vi == 0 ? A : (W.vi == 1 ? B : C);
-                const int ct = W.ti == 0 ? A : (W.ti == 1 ? B : C);
-                const int v = W.vs * cv + W.vo, t = W.ts * ct + W.to;
-                const int lamX = lamX0 + W.lxV * v;
-                const int offX = (riX[lamX] + v - max(0, lamX - TXc)) * pgX + t;
-                wr[offX] = res;
-                if (cmp) {
-                    const double dd = fabs(res - cmp[offX]);
-                    err = (err < dd) ? dd : err;
+            }
+            double res[NPL];
+#pragma unroll
+            for (int k = 0; k < NPL; k++) {
+                const int C = C0 - 32 * k;
+                double uA = EIK_INF, uB = EIK_INF, uC = EIK_INF;
+                if (valid[k]) {
+                    uA = shPrev[sab + 32 * k - dpitch];
+                    uB = shPrev[sab + 32 * k - dir];
+                    if ((unsigned)(C - dir) < (unsigned)dC) uC = shPrev[sab + 32 * k];
+                }
+                double a1 = eik_min(uA, dA_[k]), a2 = eik_min(uB, dB_[k]), a3 = eik_min(uC, dC_[k]);
+                res[k] = own[k];
+                const double amin = eik_min(eik_min(a1, a2), a3);
+                if (amin < own[k]) {
+                    const double un = eik_solve3_pre(a1, a2, a3, fv[k] * h, fv[k] * fv[k] * h * h);
+                    if (un < own[k]) res[k] = un;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NPL; k++) {
+                if (valid[k]) {
+                    const int B = B0 + 32 * k, C = C0 - 32 * k;
+                    shCur[sab + 32 * k] = res[k];
+                    // position in the next sweep's layout
+                    const int cv = W.vi == 0 ? A : (W.vi == 1 ? B : C);
+                    const int ct = W.ti == 0 ? A : (W.ti == 1 ? B : C);
+                    const int v = W.vs * cv + W.vo, t = W.ts * ct + W.to;
+                    const int lamX = lamX0 + W.lxV * v;
+                    const int offX = (riX[lamX] + v - max(0, lamX - TXc)) * pgX + t;
+                    wr[offX] = res[k];
+                    if (cmp) {
+                        const double dd = fabs(res[k] - cmp[offX]);
+                        err = (err < dd) ? dd : err;
+                    }
                 }
             }
         }
@@ -118,7 +147,7 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
 
 // bufs: S x 3 x Mmax doubles; buffer 0 of every source holds u0 in layout L0 on entry.
 // where[src] receives the index (0..2) of the buffer holding the result (layout L0).
-template <int NT>
+template <int NT, int NPL>
 __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__restrict__ bufs,
                                                     const double *__restrict__ flay, const double h,
                                                     const double tol, const int max_rounds, const int S,
@@ -143,14 +172,14 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
         while (r < max_rounds) {
             double err = 0.0;
             double *Bo = B3 + o * N, *Ba = B3 + a * N, *Bb = B3 + b * N;
-            sweep3d_v1<NT>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT, NPL>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT, NPL>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT, NPL>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT, NPL>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT, NPL>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT, NPL>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT, NPL>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT, NPL>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, ri, riStride, err);
             const double e = block_max<NT>(err, red);
             if (threadIdx.x == 0 && errs) errs[(long long)src * max_rounds + r] = e;
             r++;

@@ -143,45 +143,37 @@ __device__ __forceinline__ unsigned adj_axis_code(const double *u, long long id,
     return (ui > a) ? (unsigned)side : 0u;
 }
 
-// Elementwise over S*N nodes.
+// Elementwise; grid = (blocks, S): 32-bit index math only (64-bit div/mod dominated the first version).
 __global__ void k_adj3d_setup(const double *__restrict__ U, const double *__restrict__ U0,
                               const double *__restrict__ G, double *__restrict__ X, double *__restrict__ GU0,
                               unsigned char *__restrict__ code, int *__restrict__ remaining, const Dims3 d,
                               const int S) {
-    const long long total = d.N * S;
-    const long long stride_i = (long long)d.n * d.l;
-    int mine = -1, mycount = 0;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total;
-         q += (long long)gridDim.x * blockDim.x) {
-        const int src = (int)(q / d.N);
-        const long long id = q - (long long)src * d.N;
-        const double *u = U + (long long)src * d.N;
+    const int src = blockIdx.y;
+    const long long base = (long long)src * d.N;
+    const double *u = U + base;
+    const int N = (int)d.N, n = d.n, l = d.l, nl = d.n * d.l;
+    int mycount = 0;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < N; id += gridDim.x * blockDim.x) {
         const double ui = u[id];
-        const bool same = (ui == U0[q]);
-        if (GU0) GU0[q] = same ? G[q] : 0.0;
+        const bool same = (ui == U0[base + id]);
+        if (GU0) GU0[base + id] = same ? G[base + id] : 0.0;
         unsigned cd;
         if (same) cd = ADJ_PIN | ADJ_DONE;
         else {
-            const int k = (int)(id % d.l);
-            const long long t = id / d.l;
-            const int j = (int)(t % d.n);
-            const int i = (int)(t / d.n);
-            cd = adj_axis_code(u, id, i, d.m, stride_i, ui) | (adj_axis_code(u, id, j, d.n, d.l, ui) << 2) |
-                 (adj_axis_code(u, id, k, d.l, 1, ui) << 4);
+            const int i = id / nl;
+            const int r = id - i * nl;
+            const int j = r / l;
+            const int k = r - j * l;
+            cd = adj_axis_code(u, id, i, d.m, nl, ui) | (adj_axis_code(u, id, j, n, l, ui) << 2) |
+                 (adj_axis_code(u, id, k, l, 1, ui) << 4);
             if (cd == 0) cd = ADJ_PIN | ADJ_DONE;
         }
-        code[q] = (unsigned char)cd;
-        X[q] = 0.0;
-        if (!(cd & ADJ_DONE)) {
-            if (src != mine) {
-                if (mycount) atomicAdd(&remaining[mine], mycount);
-                mine = src;
-                mycount = 0;
-            }
-            mycount++;
-        }
+        code[base + id] = (unsigned char)cd;
+        X[base + id] = 0.0;
+        if (!(cd & ADJ_DONE)) mycount++;
     }
-    if (mycount) atomicAdd(&remaining[mine], mycount);
+    for (int o = 16; o > 0; o >>= 1) mycount += __shfl_xor_sync(0xffffffffu, mycount, o);
+    if ((threadIdx.x & 31) == 0 && mycount) atomicAdd(&remaining[src], mycount);
 }
 
 template <int NT>
