@@ -134,7 +134,7 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     const char *fv0 = getenv("ADTOMO_FORCE_V0");
     c->force_v0 = (fv0 && fv0[0] == '1');
     const char *fvv = getenv("ADTOMO_FWD_VARIANT");
-    c->fwd_variant = fvv ? atoi(fvv) : 1;
+    c->fwd_variant = fvv ? atoi(fvv) : 0;
     *out = c;
     return 0;
 }
@@ -244,28 +244,42 @@ static int get_plan(adtomo_ctx *c, int m, int n, int l, PlanCache **out) {
     PlanCache *pc = new PlanCache();
     pc->m = m; pc->n = n; pc->l = l;
     if (!build_plan(pc->hp, m, n, l)) { delete pc; return fail(ADTOMO_ERR_ARG, "internal: layout plan construction failed for %dx%dx%d", m, n, l); }
-    size_t total = 0;
-    for (int q = 0; q < NLAYOUT; q++) total += pc->hp.lay[q].rowIndex.size();
-    std::vector<int> host(total);
-    CK(cudaMalloc(&pc->d_tables, sizeof(int) * total));
+    // device copies of the tables: [rowIndex | fcum] as ints, then tOf as 16-bit
+    size_t total = 0, total16 = 0;
+    for (int q = 0; q < NLAYOUT; q++) {
+        total += pc->hp.lay[q].rowIndex.size() + pc->hp.lay[q].fcum.size();
+        total16 += pc->hp.lay[q].tOf.size();
+    }
+    const size_t bytes = sizeof(int) * total + sizeof(unsigned short) * total16;
+    std::vector<unsigned char> host(bytes);
+    CK(cudaMalloc(&pc->d_tables, bytes));
     pc->dev = pc->hp.plan;
-    size_t o = 0;
+    int *hi = (int *)host.data();
+    unsigned short *hs = (unsigned short *)(host.data() + sizeof(int) * total);
+    int *di = pc->d_tables;
+    unsigned short *ds = (unsigned short *)((unsigned char *)pc->d_tables + sizeof(int) * total);
+    size_t o = 0, o16 = 0;
     for (int q = 0; q < NLAYOUT; q++) {
         auto &H = pc->hp.lay[q];
-        memcpy(&host[o], H.rowIndex.data(), sizeof(int) * H.rowIndex.size());
-        pc->dev.lay[q].rowIndex = pc->d_tables + o;
+        memcpy(hi + o, H.rowIndex.data(), sizeof(int) * H.rowIndex.size());
+        pc->dev.lay[q].rowIndex = di + o;
         o += H.rowIndex.size();
+        memcpy(hi + o, H.fcum.data(), sizeof(int) * H.fcum.size());
+        pc->dev.lay[q].fcum = di + o;
+        o += H.fcum.size();
+        memcpy(hs + o16, H.tOf.data(), sizeof(unsigned short) * H.tOf.size());
+        pc->dev.lay[q].tOf = ds + o16;
+        o16 += H.tOf.size();
     }
-    CK(cudaMemcpy(pc->d_tables, host.data(), sizeof(int) * total, cudaMemcpyHostToDevice));
-    int ris = 0;
-    for (int q = 0; q < NLAYOUT; q++) ris = std::max(ris, pc->dev.lay[q].nlev + 1);
-    size_t prog = 0;
+    CK(cudaMemcpy(pc->d_tables, host.data(), bytes, cudaMemcpyHostToDevice));
+    int ris = 0, fcLen = 0, tLen = 0;
     for (int q = 0; q < NLAYOUT; q++) {
-        int sl = 0;
-        while ((32 << sl) < pc->dev.lay[q].dB) sl++;
-        prog = std::max(prog, ((size_t)(pc->dev.lay[q].dA + 2) << sl) + 1);
+        ris = std::max(ris, pc->dev.lay[q].nlev + 1);
+        fcLen = std::max(fcLen, pc->dev.lay[q].dB + pc->dev.lay[q].dC);
+        tLen = std::max(tLen, pc->dev.lay[q].dB * pc->dev.lay[q].dC);
     }
-    pc->smem_bytes = sizeof(double) * 2 * (size_t)pc->dev.sheet + sizeof(int) * ((size_t)NLAYOUT * ris + prog + 8);
+    pc->smem_bytes = sizeof(double) * 2 * (size_t)pc->dev.sheet + sizeof(int) * ((size_t)NLAYOUT * ris + fcLen) +
+                     sizeof(unsigned short) * (size_t)tLen + 16;
     c->plans.push_back(pc);
     *out = pc;
     return 0;

@@ -27,33 +27,30 @@ namespace adtomo {
 // One directional sweep.  shA/shB: two (dA+2) x pitch sheets with a +inf border (a missing upwind
 // neighbour then reads +inf and min() returns the existing one: the reference's mirror rule,
 // Eikonal3D.cpp:47-52).  ri: shared-memory copy of the layouts' rowIndex tables, stride riStride.
-// NPL = nodes per lane and work item: a warp handles a 32*NPL-wide piece of a row, lane l owning the
-// minor coordinates B0+l, B0+l+32, ...; the NPL updates are independent and interleave (ILP), and the
-// per-item index arithmetic is amortised over NPL nodes.
+// fcS/tOfS: shared-memory scratch for the current layout's packed-enumeration tables.
+// The nodes of a level are enumerated PACKED (rows concatenated, see layouts.h): lane q of the level
+// finds its row through tOf, so every warp item is full no matter how short the rows of the level
+// are (row-wise items left 36 % of the lanes idle on 128x128x64).  NPL = nodes per lane and item:
+// the NPL updates are independent and interleave (ILP).
 template <int NT, int NPL>
 __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const double *rd, double *wr,
                                            const double *__restrict__ fl, const double *cmp, const double h,
                                            double *shA, double *shB, const int *ri, const int riStride,
-                                           double &err) {
+                                           int *fcS, unsigned short *tOfS, double &err) {
     const SweepDev W = P.sw[sw];
     const LayoutDev &L = P.lay[W.rl];
     const LayoutDev &X = P.lay[W.wl];
     const int dir = W.dir;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NW = NT / 32;
     const int dA = L.dA, dB = L.dB, dC = L.dC, pitch = L.pitch, pg = L.pg, nlev = L.nlev;
     const int T = dB + dC - 2;
     const int *riL = ri + W.rl * riStride;
     const int *riX = ri + W.wl * riStride;
-    // a warp owns one (32*NPL)-wide segment of minor coordinates (loop invariant) and strides over rows
-    int sl = 0;
-    while (((32 * NPL) << sl) < dB) sl++;
-    const int B0 = ((warp & ((1 << sl) - 1)) * (32 * NPL)) + lane;
-    const int row0 = warp >> sl, rowStep = NW >> sl;
     const int dpg = dir * pg, dpitch = dir * pitch;
     const int TXc = (X.dB - 1) + (X.dC - 1);
     const int pgX = X.pg;
-    // +inf borders for this layout's sheet geometry
+    // tables of this layout, +inf borders for this layout's sheet geometry
+    for (int q = threadIdx.x; q < T + 2; q += NT) fcS[q] = L.fcum[q];
+    for (int q = threadIdx.x; q < dB * dC; q += NT) tOfS[q] = L.tOf[q];
     for (int q = threadIdx.x; q < pitch; q += NT) {
         shA[q] = EIK_INF; shB[q] = EIK_INF;
         shA[(dA + 1) * pitch + q] = EIK_INF; shB[(dA + 1) * pitch + q] = EIK_INF;
@@ -67,36 +64,43 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
     for (int step = 0; step < nlev; step++) {
         const int lam = dir > 0 ? step : nlev - 1 - step;
         const int Alo = max(0, lam - T), Ahi = min(dA - 1, lam);
+        const int q0 = fcS[lam - Ahi];                       // packed index of the level's first node
+        const int cnt = fcS[lam - Alo + 1] - q0;             // nodes in the level
         const int lamD = lam + dir;
         const bool hasD = (unsigned)lamD < (unsigned)nlev;
-        const int base0 = (riL[lam] - Alo) * pg + B0;
-        const int baseD = hasD ? (riL[lamD] - max(0, lamD - T)) * pg + B0 : 0;
+        const int base0 = (riL[lam] - Alo) * pg;
+        const int baseD = hasD ? (riL[lamD] - max(0, lamD - T)) * pg : 0;
         const int lamP = lam + 2 * dir;
         const bool hasP = (unsigned)lamP < (unsigned)nlev;
-        const int baseP = hasP ? (riL[lamP] - max(0, lamP - T)) * pg + B0 : 0;
+        const int baseP = hasP ? (riL[lamP] - max(0, lamP - T)) * pg : 0;
         const int lamX0 = W.lx0 + W.lxL * lam;
-        for (int A = Alo + row0; A <= Ahi; A += rowStep) {
-            const int ab = A * pg;
-            const int sab = (A + 1) * pitch + B0 + 1;
-            const int C0 = lam - A - B0;
-            const bool hDA = (unsigned)(A + dir) < (unsigned)dA;
+        for (int item = threadIdx.x; item < cnt; item += NT * NPL) {
             bool valid[NPL];
+            int A_[NPL], B_[NPL], C_[NPL];
             double own[NPL], fv[NPL], dA_[NPL], dB_[NPL], dC_[NPL];
 #pragma unroll
             for (int k = 0; k < NPL; k++) {
-                const int B = B0 + 32 * k, C = C0 - 32 * k;
-                valid[k] = (B < dB) && ((unsigned)C < (unsigned)dC);
+                // lanes of a warp take 32 consecutive nodes; the warp's NPL groups are NT apart
+                const int q = item + k * NT;
+                valid[k] = q < cnt;
                 own[k] = 0.0; fv[k] = 0.0; dA_[k] = EIK_INF; dB_[k] = EIK_INF; dC_[k] = EIK_INF;
+                A_[k] = 0; B_[k] = 0; C_[k] = 0;
                 if (valid[k]) {
-                    own[k] = rd[base0 + ab + 32 * k];
-                    fv[k] = fl[base0 + ab + 32 * k];
-                    const int dn = baseD + ab + 32 * k;
-                    if (hDA) dA_[k] = rd[dn + dpg];
+                    const int e = q0 + q;
+                    const int t = tOfS[e];
+                    const int B = max(0, t - (dC - 1)) + (e - fcS[t]);
+                    const int A = lam - t, C = t - B;
+                    A_[k] = A; B_[k] = B; C_[k] = C;
+                    const int ab = A * pg + B;
+                    own[k] = rd[base0 + ab];
+                    fv[k] = fl[base0 + ab];
+                    const int dn = baseD + ab;
+                    if ((unsigned)(A + dir) < (unsigned)dA) dA_[k] = rd[dn + dpg];
                     if ((unsigned)(B + dir) < (unsigned)dB) dB_[k] = rd[dn + dir];
                     if ((unsigned)(C + dir) < (unsigned)dC) dC_[k] = rd[dn];
                     // pull the level after next towards L1 (first used as downwind data of the next step)
                     if (hasP && (unsigned)(C + 2 * dir) < (unsigned)dC) {
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(rd + baseP + ab + 32 * k));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(rd + baseP + ab));
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(fl + dn));
                     }
                 }
@@ -104,12 +108,12 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
             double res[NPL];
 #pragma unroll
             for (int k = 0; k < NPL; k++) {
-                const int C = C0 - 32 * k;
+                const int sab = (A_[k] + 1) * pitch + B_[k] + 1;
                 double uA = EIK_INF, uB = EIK_INF, uC = EIK_INF;
                 if (valid[k]) {
-                    uA = shPrev[sab + 32 * k - dpitch];
-                    uB = shPrev[sab + 32 * k - dir];
-                    if ((unsigned)(C - dir) < (unsigned)dC) uC = shPrev[sab + 32 * k];
+                    uA = shPrev[sab - dpitch];
+                    uB = shPrev[sab - dir];
+                    if ((unsigned)(C_[k] - dir) < (unsigned)dC) uC = shPrev[sab];
                 }
                 double a1 = eik_min(uA, dA_[k]), a2 = eik_min(uB, dB_[k]), a3 = eik_min(uC, dC_[k]);
                 res[k] = own[k];
@@ -122,8 +126,8 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
 #pragma unroll
             for (int k = 0; k < NPL; k++) {
                 if (valid[k]) {
-                    const int B = B0 + 32 * k, C = C0 - 32 * k;
-                    shCur[sab + 32 * k] = res[k];
+                    const int A = A_[k], B = B_[k], C = C_[k];
+                    shCur[(A + 1) * pitch + B + 1] = res[k];
                     // position in the next sweep's layout
                     const int cv = W.vi == 0 ? A : (W.vi == 1 ? B : C);
                     const int ct = W.ti == 0 ? A : (W.ti == 1 ? B : C);
@@ -159,6 +163,13 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
     int *ri = (int *)(sheets + 2 * (size_t)P.sheet);
     int riStride = 0;
     for (int q = 0; q < NLAYOUT; q++) riStride = max(riStride, P.lay[q].nlev + 1);
+    int *fcS = ri + NLAYOUT * riStride;
+    int fcLen = 0, tLen = 0;
+    for (int q = 0; q < NLAYOUT; q++) {
+        fcLen = max(fcLen, P.lay[q].dB + P.lay[q].dC);
+        tLen = max(tLen, P.lay[q].dB * P.lay[q].dC);
+    }
+    unsigned short *tOfS = (unsigned short *)(fcS + fcLen);
     for (int q = 0; q < NLAYOUT; q++)
         for (int t = threadIdx.x; t <= P.lay[q].nlev; t += NT) ri[q * riStride + t] = P.lay[q].rowIndex[t];
     __syncthreads();
@@ -172,14 +183,14 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
         while (r < max_rounds) {
             double err = 0.0;
             double *Bo = B3 + o * N, *Ba = B3 + a * N, *Bb = B3 + b * N;
-            sweep3d_v1<NT, NPL>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT, NPL>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT, NPL>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT, NPL>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT, NPL>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT, NPL>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT, NPL>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, ri, riStride, err);
-            sweep3d_v1<NT, NPL>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, ri, riStride, err);
+            sweep3d_v1<NT, NPL>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, ri, riStride, fcS, tOfS, err);
             const double e = block_max<NT>(err, red);
             if (threadIdx.x == 0 && errs) errs[(long long)src * max_rounds + r] = e;
             r++;

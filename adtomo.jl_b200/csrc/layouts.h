@@ -38,6 +38,11 @@ struct LayoutDev {
     int pg;              // row pitch in global memory (dB rounded up to a multiple of 4)
     int M;               // slots of one field in this layout = (number of rows) * pg  (>= N)
     const int *rowIndex; // [nlev+1]   index of the first row of a level (rows of a level: A = Alo..Ahi)
+    // packed enumeration of a level: its rows, ordered by t = lam - A ascending, are concatenated;
+    // fcum[t] = number of nodes in rows 0..t-1 of the full t-range [0, dB+dC-2] (a level uses a
+    // sub-range tmin..tmax), tOf[e] = the row t containing packed index e in [0, dB*dC).
+    const int *fcum;             // [dB+dC]
+    const unsigned short *tOf;   // [dB*dC]
 };
 
 struct SweepDev {
@@ -81,8 +86,9 @@ LAY_HD int lay_offset(const LayoutDev &L, const int *ext, int xi, int xj, int xk
 // host-side construction
 // ---------------------------------------------------------------------------------------------
 struct HostLayout {
-    LayoutDev d;                  // rowIndex points into the vector below
-    std::vector<int> rowIndex;
+    LayoutDev d;                  // table pointers point into the vectors below
+    std::vector<int> rowIndex, fcum;
+    std::vector<unsigned short> tOf;
 };
 
 inline void build_layout(HostLayout &H, const int ext[3], const int sign[3], int major) {
@@ -110,6 +116,18 @@ inline void build_layout(HostLayout &H, const int ext[3], const int sign[3], int
     H.rowIndex[L.nlev] = acc;
     L.M = acc * L.pg;
     L.rowIndex = H.rowIndex.data();
+    const int T = L.dB + L.dC - 2;
+    H.fcum.assign(T + 2, 0);
+    H.tOf.assign((size_t)L.dB * L.dC, 0);
+    int c = 0;
+    for (int t = 0; t <= T; t++) {
+        H.fcum[t] = c;
+        const int lo = lay_imax(0, t - (L.dC - 1)), hi = lay_imin(L.dB - 1, t);
+        for (int b = lo; b <= hi; b++) H.tOf[c++] = (unsigned short)t;
+    }
+    H.fcum[T + 1] = c;
+    L.fcum = H.fcum.data();
+    L.tOf = H.tOf.data();
 }
 
 struct HostPlan {
@@ -131,6 +149,7 @@ inline bool build_plan(HostPlan &HP, int m, int n, int l) {
         build_layout(HP.lay[q], P.ext, signs[q], majors[q]);
         P.lay[q] = HP.lay[q].d;
         if (HP.lay[q].rowIndex.back() != P.lay[q].dA * (P.lay[q].dB + P.lay[q].dC - 1)) return false;
+        if (HP.lay[q].fcum.back() != P.lay[q].dB * P.lay[q].dC || P.lay[q].dB + P.lay[q].dC > 65535) return false;
         P.sheet = lay_imax(P.sheet, (P.lay[q].dA + 2) * P.lay[q].pitch);
         P.Mmax = lay_imax(P.Mmax, P.lay[q].M);
     }

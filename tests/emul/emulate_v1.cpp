@@ -31,10 +31,18 @@ static void sweep(const Plan3 &P, int sw, const double *rd, double *wr, const do
         const int lamD = lam + dir;
         const bool hasD = lamD >= 0 && lamD < nlev;
         const int lamX0 = W.lx0 + W.lxL * lam;
-        for (int A = Alo; A <= Ahi; A++)
-            for (int B = 0; B < dB; B++) {
-                const int C = lam - A - B;
-                if (C < 0 || C >= dC) continue;
+        const int T = dB + dC - 2;
+        const int q0 = L.fcum[lam - Ahi], cnt = L.fcum[lam - Alo + 1] - q0;
+        int seen = 0;
+        for (int q = 0; q < cnt; q++) {
+            {
+                // packed enumeration exactly as in the kernel
+                const int e = q0 + q;
+                const int t = L.tOf[e];
+                const int B = std::max(0, t - (dC - 1)) + (e - L.fcum[t]);
+                const int A = lam - t, C = t - B;
+                if (A < Alo || A > Ahi || B < 0 || B >= dB || C < 0 || C >= dC || t > T) { err = NAN; continue; }
+                seen++;
                 const int base0 = (L.rowIndex[lam] - Alo) * pg + B;
                 const int baseD = hasD ? (L.rowIndex[lamD] - std::max(0, lamD - (dB - 1) - (dC - 1))) * pg + B : 0;
                 const int ab = A * pg, sab = (A + 1) * pitch + B + 1;
@@ -58,12 +66,19 @@ static void sweep(const Plan3 &P, int sw, const double *rd, double *wr, const do
                 }
                 shCur[sab] = res;
                 const int cv = W.vi == 0 ? A : (W.vi == 1 ? B : C), ct = W.ti == 0 ? A : (W.ti == 1 ? B : C);
-                const int v = W.vs * cv + W.vo, t = W.ts * ct + W.to;
+                const int v = W.vs * cv + W.vo, tt = W.ts * ct + W.to;
                 const int lamX = lamX0 + W.lxV * v;
-                const int offX = (X.rowIndex[lamX] + v - std::max(0, lamX - TXc)) * X.pg + t;
+                const int offX = (X.rowIndex[lamX] + v - std::max(0, lamX - TXc)) * X.pg + tt;
                 wr[offX] = res;
                 if (cmp) err = std::max(err, std::fabs(res - cmp[offX]));
             }
+        }
+        {   // the packed enumeration must cover the level exactly once
+            int expect = 0;
+            for (int A = Alo; A <= Ahi; A++)
+                for (int B = 0; B < dB; B++) { const int C = lam - A - B; if (C >= 0 && C < dC) expect++; }
+            if (expect != seen) err = NAN;
+        }
         std::swap(shPrev, shCur);
     }
 }
