@@ -364,13 +364,25 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
         k_adj3d_count<<<dim3(std::min(elem_grid(c, d.N), 128), S), 256, 0, c->stream>>>(code, cnt, Q, cnts + S, d, S);
         phase_end(c, pk);
         LAUNCHED(c, "k_adj3d_count");
-        int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo<NT3>, NT3, 0));
-        if (occ < 1) occ = 1;
-        int grid = std::min(S, c->num_sms * occ);
+        // threads per source: as many as keep all sources of the batch resident at once
+        const char *ev = getenv("ADTOMO_ADJ_NT");
+        int nt = ev ? atoi(ev) : 0;
+        if (nt != 256 && nt != 512 && nt != 768 && nt != 1024) nt = 1024;   // measured best on the 256-source batch
+        auto launch = [&](auto kern, int NTv) -> int {
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTv, 0));
+            if (occ < 1) occ = 1;
+            int grid = std::min(S, c->num_sms * occ);
+            kern<<<grid, NTv, 0, c->stream>>>(dU, dG, X, code, (unsigned int *)cnt, Q, cnts + S, cnts, d, S, d_status);
+            return 0;
+        };
         pk = phase_begin(c, PH_ADJ_SWEEP);
-        k_adj3d_topo<NT3><<<grid, NT3, 0, c->stream>>>(dU, dG, X, code, (unsigned int *)cnt, Q, cnts + S, cnts, d,
-                                                        S, d_status);
+        int lrc = 0;
+        if (nt == 256) lrc = launch(k_adj3d_topo<256>, 256);
+        else if (nt == 512) lrc = launch(k_adj3d_topo<512>, 512);
+        else if (nt == 768) lrc = launch(k_adj3d_topo<768>, 768);
+        else lrc = launch(k_adj3d_topo<1024>, 1024);
+        if (lrc) return lrc;
         phase_end(c, pk);
         LAUNCHED(c, "k_adj3d_topo");
         pk = phase_begin(c, PH_ADJ_FINISH);

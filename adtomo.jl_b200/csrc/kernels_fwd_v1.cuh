@@ -32,7 +32,7 @@ namespace adtomo {
 // finds its row through tOf, so every warp item is full no matter how short the rows of the level
 // are (row-wise items left 36 % of the lanes idle on 128x128x64).  NPL = nodes per lane and item:
 // the NPL updates are independent and interleave (ILP).
-template <int NT, int NPL>
+template <int NT, int NPL, int DIR>
 __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const double *rd, double *wr,
                                            const double *__restrict__ fl, const double *cmp, const double h,
                                            double *shA, double *shB, const int *ri, const int riStride,
@@ -40,7 +40,7 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
     const SweepDev W = P.sw[sw];
     const LayoutDev &L = P.lay[W.rl];
     const LayoutDev &X = P.lay[W.wl];
-    const int dir = W.dir;
+    constexpr int dir = DIR;   // sweeps 1-4 ascend, 5-8 descend the levels of their layout (layouts.h)
     const int dA = L.dA, dB = L.dB, dC = L.dC, pitch = L.pitch, pg = L.pg, nlev = L.nlev;
     const int T = dB + dC - 2;
     const int *riL = ri + W.rl * riStride;
@@ -117,9 +117,9 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
                 }
                 double a1 = eik_min(uA, dA_[k]), a2 = eik_min(uB, dB_[k]), a3 = eik_min(uC, dC_[k]);
                 res[k] = own[k];
-                const double amin = eik_min(eik_min(a1, a2), a3);
-                if (amin < own[k]) {
-                    const double un = eik_solve3_pre(a1, a2, a3, fv[k] * h, fv[k] * fv[k] * h * h);
+                eik_sort3(a1, a2, a3);
+                if (a1 < own[k]) {   // otherwise the candidate (> a1) cannot win the min: exact skip
+                    const double un = eik_solve3_sorted(a1, a2, a3, fv[k] * h, fv[k] * fv[k] * h * h);
                     if (un < own[k]) res[k] = un;
                 }
             }
@@ -183,14 +183,14 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
         while (r < max_rounds) {
             double err = 0.0;
             double *Bo = B3 + o * N, *Ba = B3 + a * N, *Bb = B3 + b * N;
-            sweep3d_v1<NT, NPL>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL, 1>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL, 1>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL, 1>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL, 1>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL, -1>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL, -1>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL, -1>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
+            sweep3d_v1<NT, NPL, -1>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, ri, riStride, fcS, tOfS, err);
             const double e = block_max<NT>(err, red);
             if (threadIdx.x == 0 && errs) errs[(long long)src * max_rounds + r] = e;
             r++;
