@@ -51,6 +51,7 @@ struct adtomo_ctx {
     std::vector<std::pair<int, int>> ev_used;   // (phase, pool index)
     std::vector<struct PlanCache *> plans;      // level-major layout plans, one per grid shape
     int fwd_variant = 0;                        // tuning aid: ADTOMO_FWD_VARIANT selects <threads, nodes per lane>
+    int force_cluster = 0;                      // testing aid: ADTOMO_FORCE_CLUSTER=2|4|8 splits every source over a cluster
     int force_v0 = 0;                           // debugging aid: ADTOMO_FORCE_V0=1 selects the row-major kernel
 };
 
@@ -135,6 +136,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     c->force_v0 = (fv0 && fv0[0] == '1');
     const char *fvv = getenv("ADTOMO_FWD_VARIANT");
     c->fwd_variant = fvv ? atoi(fvv) : 0;
+    const char *fcl = getenv("ADTOMO_FORCE_CLUSTER");
+    c->force_cluster = fcl ? atoi(fcl) : 0;
     *out = c;
     return 0;
 }
@@ -272,16 +275,65 @@ static int get_plan(adtomo_ctx *c, int m, int n, int l, PlanCache **out) {
         o16 += H.tOf.size();
     }
     CK(cudaMemcpy(pc->d_tables, host.data(), bytes, cudaMemcpyHostToDevice));
-    int ris = 0, fcLen = 0, tLen = 0;
-    for (int q = 0; q < NLAYOUT; q++) {
-        ris = std::max(ris, pc->dev.lay[q].nlev + 1);
-        fcLen = std::max(fcLen, pc->dev.lay[q].dB + pc->dev.lay[q].dC);
-        tLen = std::max(tLen, pc->dev.lay[q].dB * pc->dev.lay[q].dC);
-    }
-    pc->smem_bytes = sizeof(double) * 2 * (size_t)pc->dev.sheet + sizeof(int) * ((size_t)NLAYOUT * ris + fcLen) +
-                     sizeof(unsigned short) * (size_t)tLen + 16;
+    pc->smem_bytes = 0;
     c->plans.push_back(pc);
     *out = pc;
+    return 0;
+}
+
+// Shared-memory need of k_fwd3d_v1 when a source is split over a cluster of CS CTAs.
+struct FwdCfg { int CS; int sheet; int tOfSmem; size_t smem; };
+static bool fwd_config(const PlanCache *pc, int CS, FwdCfg *out) {
+    int sheet = 0, ris = 0, fcLen = 0, tLen = 0;
+    for (int q = 0; q < NLAYOUT; q++) {
+        const LayoutDev &L = pc->dev.lay[q];
+        if (L.dB > 256 * 32) return false;
+        if (L.dA < CS) return false;
+        sheet = std::max(sheet, ((L.dA + CS - 1) / CS + 2) * L.pitch);
+        ris = std::max(ris, L.nlev + 1);
+        fcLen = std::max(fcLen, L.dB + L.dC);
+        tLen = std::max(tLen, L.dB * L.dC);
+    }
+    size_t base = sizeof(double) * 2 * (size_t)sheet + sizeof(int) * ((size_t)NLAYOUT * ris + fcLen) + 16;
+    size_t withT = base + sizeof(unsigned short) * (size_t)tLen;
+    if (base > SMEM_MAX_DYN) return false;
+    out->CS = CS;
+    out->sheet = sheet;
+    out->tOfSmem = withT <= SMEM_MAX_DYN;
+    out->smem = out->tOfSmem ? withT : base;
+    return true;
+}
+
+template <typename K>
+static int launch_fwd(adtomo_ctx *c, K kern, int NT, const FwdCfg &cfg, const PlanCache *pc, double *bufs,
+                      const double *flay, double h, double tol, int max_rounds, int S, int *d_rounds, double *d_errs,
+                      int *where, double *errPart) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
+    cudaLaunchConfig_t lc = {};
+    lc.blockDim = dim3(NT);
+    lc.dynamicSmemBytes = cfg.smem;
+    lc.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    int nattr = 0;
+    int nsrc = std::min(S, c->num_sms / cfg.CS);
+    if (cfg.CS > 1) {
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cfg.CS;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        nattr = 1;
+        lc.attrs = at;
+        lc.numAttrs = nattr;
+        lc.gridDim = dim3(cfg.CS * nsrc);
+        int maxc = 0;
+        if (cudaOccupancyMaxActiveClusters(&maxc, kern, &lc) == cudaSuccess && maxc > 0) nsrc = std::min(nsrc, maxc);
+        else cudaGetLastError();
+    }
+    lc.gridDim = dim3(cfg.CS * nsrc);
+    lc.attrs = nattr ? at : nullptr;
+    lc.numAttrs = nattr;
+    CK(cudaLaunchKernelEx(&lc, kern, pc->dev, cfg.sheet, cfg.tOfSmem, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs,
+                          where, errPart));
     return 0;
 }
 
@@ -291,23 +343,17 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
     PlanCache *pc = nullptr;
     int rc = get_plan(c, d.m, d.n, d.l, &pc);
     if (rc) return rc;
-    bool fits = pc->smem_bytes <= SMEM_MAX_DYN;
-    for (int q = 0; q < NLAYOUT; q++) fits = fits && pc->dev.lay[q].dB <= 256;   // at most 8 segments per row (wait loop uses 3*nseg lanes)
+    FwdCfg cfg;
+    bool fits = false;
+    for (int cs = std::max(1, c->force_cluster); cs <= 8 && !fits; cs *= 2) fits = fwd_config(pc, cs, &cfg);
     if (!c->force_v0 && fits) {
         // level-major path: convert in, sweep, convert out
-        double *bufs, *flay;
+        double *bufs, *flay, *errPart;
         int *where;
         WS(c, "fwd_bufs", double, (size_t)S * 3 * pc->dev.Mmax, bufs);
         WS(c, "fwd_flay", double, (size_t)NLAYOUT * pc->dev.Mmax, flay);
         WS(c, "fwd_where", int, S, where);
-        static bool attr_set = false;
-        if (!attr_set) {
-            CK(cudaFuncSetAttribute(k_fwd3d_v1<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
-            CK(cudaFuncSetAttribute(k_fwd3d_v1<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
-            CK(cudaFuncSetAttribute(k_fwd3d_v1<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
-            CK(cudaFuncSetAttribute(k_fwd3d_v1<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
-            attr_set = true;
-        }
+        WS(c, "fwd_errpart", double, (size_t)S * 8, errPart);
         int pk = phase_begin(c, PH_CONVERT);
         const int eb = elem_grid(c, d.N);
         k_f_to_layouts<<<eb, 256, 0, c->stream>>>(pc->dev, df, flay);
@@ -315,14 +361,14 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         k_u0_to_L0<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(pc->dev, dU, bufs);
         phase_end(c, pk);
         LAUNCHED(c, "k_u0_to_L0");
-        int grid = std::min(S, c->num_sms);
         pk = phase_begin(c, PH_FWD);
-        switch (c->fwd_variant) {
-            case 1: k_fwd3d_v1<1024, 2><<<grid, 1024, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where); break;
-            case 2: k_fwd3d_v1<512, 2><<<grid, 512, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where); break;
-            case 3: k_fwd3d_v1<512, 1><<<grid, 512, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where); break;
-            default: k_fwd3d_v1<1024, 1><<<grid, 1024, pc->smem_bytes, c->stream>>>(pc->dev, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where); break;
-        }
+        if (cfg.CS > 1)
+            rc = launch_fwd(c, k_fwd3d_v1<1024, 1, true>, 1024, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);
+        else if (c->fwd_variant == 1)
+            rc = launch_fwd(c, k_fwd3d_v1<1024, 2, false>, 1024, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);
+        else
+            rc = launch_fwd(c, k_fwd3d_v1<1024, 1, false>, 1024, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);
+        if (rc) return rc;
         phase_end(c, pk);
         LAUNCHED(c, "k_fwd3d_v1");
         pk = phase_begin(c, PH_CONVERT);

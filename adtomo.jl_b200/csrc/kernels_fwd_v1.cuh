@@ -17,6 +17,7 @@
 // Three rotating global buffers per source hold: the field at round start (for the L-inf stopping
 // test of Eikonal3D.cpp:77-85, fused into the last sweep's write phase), and the ping-pong pair.
 #pragma once
+#include <cooperative_groups.h>
 #include "kernels_v0.cuh"
 #include "layouts.h"
 
@@ -32,11 +33,17 @@ namespace adtomo {
 // finds its row through tOf, so every warp item is full no matter how short the rows of the level
 // are (row-wise items left 36 % of the lanes idle on 128x128x64).  NPL = nodes per lane and item:
 // the NPL updates are independent and interleave (ILP).
-template <int NT, int NPL, int DIR>
+// CL (cluster mode): the rows of a level are split evenly over the CS CTAs of a thread-block cluster
+// (rank r owns major coordinates [dA*r/CS, dA*(r+1)/CS)); each CTA keeps sheets for its rows plus one
+// halo row per side, pushes its boundary row into the neighbour's halo through distributed shared
+// memory, and the per-level barrier becomes a cluster barrier.  Used when two full sheets do not fit
+// one SM (e.g. 200x200x80).
+template <int NT, int NPL, int DIR, bool CL>
 __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const double *rd, double *wr,
                                            const double *__restrict__ fl, const double *cmp, const double h,
                                            double *shA, double *shB, const int *ri, const int riStride,
-                                           int *fcS, unsigned short *tOfS, double &err) {
+                                           int *fcS, const unsigned short *tOfS, const int rank, const int CS,
+                                           double &err) {
     const SweepDev W = P.sw[sw];
     const LayoutDev &L = P.lay[W.rl];
     const LayoutDev &X = P.lay[W.wl];
@@ -48,24 +55,51 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
     const int dpg = dir * pg, dpitch = dir * pitch;
     const int TXc = (X.dB - 1) + (X.dC - 1);
     const int pgX = X.pg;
-    // tables of this layout, +inf borders for this layout's sheet geometry
+    // rows owned by this CTA: [a0, a1); sheet row of A is A - a0 + 1 (rows 0 and a1-a0+1 are halos)
+    const int a0 = CL ? (dA * rank) / CS : 0;
+    const int a1 = CL ? (dA * (rank + 1)) / CS : dA;
+    const int nown = a1 - a0;
+    // tables of this layout (tOf stays in global memory when it does not fit: tOfS == nullptr)
     for (int q = threadIdx.x; q < T + 2; q += NT) fcS[q] = L.fcum[q];
-    for (int q = threadIdx.x; q < dB * dC; q += NT) tOfS[q] = L.tOf[q];
+    const unsigned short *tOfT = tOfS ? tOfS : L.tOf;
+    if (tOfS)
+        for (int q = threadIdx.x; q < dB * dC; q += NT) ((unsigned short *)tOfS)[q] = L.tOf[q];
+    // +inf borders/halos for this layout's sheet geometry
     for (int q = threadIdx.x; q < pitch; q += NT) {
         shA[q] = EIK_INF; shB[q] = EIK_INF;
-        shA[(dA + 1) * pitch + q] = EIK_INF; shB[(dA + 1) * pitch + q] = EIK_INF;
+        shA[(nown + 1) * pitch + q] = EIK_INF; shB[(nown + 1) * pitch + q] = EIK_INF;
     }
-    for (int q = threadIdx.x; q < dA + 2; q += NT) {
+    for (int q = threadIdx.x; q < nown + 2; q += NT) {
         shA[q * pitch] = EIK_INF; shB[q * pitch] = EIK_INF;
         shA[q * pitch + dB + 1] = EIK_INF; shB[q * pitch + dB + 1] = EIK_INF;
     }
-    __syncthreads();
+    double *rmA = nullptr, *rmB = nullptr;   // neighbour's sheets (the one downstream in this sweep's direction)
+    int rmRow = 0;                           // halo row of the neighbour that mirrors my boundary row
+    const int myEdge = DIR > 0 ? a1 - 1 : a0;
+    bool push = false;
+    if (CL) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        const int nb = rank + DIR;
+        if (nb >= 0 && nb < CS) {
+            push = true;
+            rmA = cluster.map_shared_rank(shA, nb);
+            rmB = cluster.map_shared_rank(shB, nb);
+            const int nb0 = (dA * nb) / CS, nb1 = (dA * (nb + 1)) / CS;
+            rmRow = DIR > 0 ? 0 : (nb1 - nb0 + 1);
+        }
+        cluster.sync();
+    } else {
+        __syncthreads();
+    }
     double *shPrev = shA, *shCur = shB;
+    double *rmCur = rmB;
     for (int step = 0; step < nlev; step++) {
         const int lam = dir > 0 ? step : nlev - 1 - step;
         const int Alo = max(0, lam - T), Ahi = min(dA - 1, lam);
-        const int q0 = fcS[lam - Ahi];                       // packed index of the level's first node
-        const int cnt = fcS[lam - Alo + 1] - q0;             // nodes in the level
+        const int Amin = max(Alo, a0), Amax = min(Ahi, a1 - 1);   // my rows in this level
+        const int q0 = Amax >= Amin ? fcS[lam - Amax] : 0;        // packed index of my first node
+        const int cnt = Amax >= Amin ? fcS[lam - Amin + 1] - q0 : 0;
         const int lamD = lam + dir;
         const bool hasD = (unsigned)lamD < (unsigned)nlev;
         const int base0 = (riL[lam] - Alo) * pg;
@@ -87,7 +121,7 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
                 A_[k] = 0; B_[k] = 0; C_[k] = 0;
                 if (valid[k]) {
                     const int e = q0 + q;
-                    const int t = tOfS[e];
+                    const int t = tOfT[e];
                     const int B = max(0, t - (dC - 1)) + (e - fcS[t]);
                     const int A = lam - t, C = t - B;
                     A_[k] = A; B_[k] = B; C_[k] = C;
@@ -108,7 +142,7 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
             double res[NPL];
 #pragma unroll
             for (int k = 0; k < NPL; k++) {
-                const int sab = (A_[k] + 1) * pitch + B_[k] + 1;
+                const int sab = (A_[k] - a0 + 1) * pitch + B_[k] + 1;
                 double uA = EIK_INF, uB = EIK_INF, uC = EIK_INF;
                 if (valid[k]) {
                     uA = shPrev[sab - dpitch];
@@ -127,7 +161,8 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
             for (int k = 0; k < NPL; k++) {
                 if (valid[k]) {
                     const int A = A_[k], B = B_[k], C = C_[k];
-                    shCur[(A + 1) * pitch + B + 1] = res[k];
+                    shCur[(A - a0 + 1) * pitch + B + 1] = res[k];
+                    if (CL && push && A == myEdge) rmCur[rmRow * pitch + B + 1] = res[k];   // DSMEM halo push
                     // position in the next sweep's layout
                     const int cv = W.vi == 0 ? A : (W.vi == 1 ? B : C);
                     const int ct = W.ti == 0 ? A : (W.ti == 1 ? B : C);
@@ -142,40 +177,48 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
                 }
             }
         }
-        __syncthreads();
+        if (CL) cooperative_groups::this_cluster().sync();
+        else __syncthreads();
         double *tmp = shPrev;
         shPrev = shCur;
         shCur = tmp;
+        rmCur = (rmCur == rmB) ? rmA : rmB;
     }
 }
 
 // bufs: S x 3 x Mmax doubles; buffer 0 of every source holds u0 in layout L0 on entry.
 // where[src] receives the index (0..2) of the buffer holding the result (layout L0).
-template <int NT, int NPL>
-__global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__restrict__ bufs,
-                                                    const double *__restrict__ flay, const double h,
-                                                    const double tol, const int max_rounds, const int S,
-                                                    int *__restrict__ rounds, double *__restrict__ errs,
-                                                    int *__restrict__ where) {
+// sheet: doubles per shared-memory sheet; tOfSmem: keep the packed-row table in shared memory.
+// CL: launched with a cluster of CS = cluster size CTAs per source; errPart: S*CS doubles.
+template <int NT, int NPL, bool CL>
+__global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, const int sheet, const int tOfSmem,
+                                                    double *__restrict__ bufs, const double *__restrict__ flay,
+                                                    const double h, const double tol, const int max_rounds,
+                                                    const int S, int *__restrict__ rounds,
+                                                    double *__restrict__ errs, int *__restrict__ where,
+                                                    double *errPart) {
     extern __shared__ double sheets[];
     __shared__ double red[NT / 32];
-    double *shA = sheets, *shB = sheets + P.sheet;
-    int *ri = (int *)(sheets + 2 * (size_t)P.sheet);
+    int rank = 0, CS = 1;
+    if (CL) {
+        cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+        rank = (int)cluster.block_rank();
+        CS = (int)cluster.num_blocks();
+    }
+    double *shA = sheets, *shB = sheets + sheet;
+    int *ri = (int *)(sheets + 2 * (size_t)sheet);
     int riStride = 0;
     for (int q = 0; q < NLAYOUT; q++) riStride = max(riStride, P.lay[q].nlev + 1);
     int *fcS = ri + NLAYOUT * riStride;
-    int fcLen = 0, tLen = 0;
-    for (int q = 0; q < NLAYOUT; q++) {
-        fcLen = max(fcLen, P.lay[q].dB + P.lay[q].dC);
-        tLen = max(tLen, P.lay[q].dB * P.lay[q].dC);
-    }
-    unsigned short *tOfS = (unsigned short *)(fcS + fcLen);
+    int fcLen = 0;
+    for (int q = 0; q < NLAYOUT; q++) fcLen = max(fcLen, P.lay[q].dB + P.lay[q].dC);
+    unsigned short *tOfS = tOfSmem ? (unsigned short *)(fcS + fcLen) : nullptr;
     for (int q = 0; q < NLAYOUT; q++)
         for (int t = threadIdx.x; t <= P.lay[q].nlev; t += NT) ri[q * riStride + t] = P.lay[q].rowIndex[t];
     __syncthreads();
     const long long N = P.Mmax;        // slots per buffer (padded rows)
     const long long MF = P.Mmax;       // slots per f layout
-    for (int src = blockIdx.x; src < S; src += gridDim.x) {
+    for (int src = blockIdx.x / CS; src < S; src += gridDim.x / CS) {
         double *B3 = bufs + (long long)src * 3 * N;
         int o = 0, a = 1, b = 2;
         int r = 0;
@@ -183,16 +226,29 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
         while (r < max_rounds) {
             double err = 0.0;
             double *Bo = B3 + o * N, *Ba = B3 + a * N, *Bb = B3 + b * N;
-            sweep3d_v1<NT, NPL, 1>(P, 0, Bo, Ba, flay + (long long)P.sw[0].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL, 1>(P, 1, Ba, Bb, flay + (long long)P.sw[1].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL, 1>(P, 2, Bb, Ba, flay + (long long)P.sw[2].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL, 1>(P, 3, Ba, Bb, flay + (long long)P.sw[3].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL, -1>(P, 4, Bb, Ba, flay + (long long)P.sw[4].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL, -1>(P, 5, Ba, Bb, flay + (long long)P.sw[5].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL, -1>(P, 6, Bb, Ba, flay + (long long)P.sw[6].rl * MF, nullptr, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            sweep3d_v1<NT, NPL, -1>(P, 7, Ba, Bb, flay + (long long)P.sw[7].rl * MF, Bo, h, shA, shB, ri, riStride, fcS, tOfS, err);
-            const double e = block_max<NT>(err, red);
-            if (threadIdx.x == 0 && errs) errs[(long long)src * max_rounds + r] = e;
+#define SWEEP(k, D, RD, WR, CMP) \
+    sweep3d_v1<NT, NPL, D, CL>(P, k, RD, WR, flay + (long long)P.sw[k].rl * MF, CMP, h, shA, shB, ri, riStride, fcS, tOfS, rank, CS, err)
+            SWEEP(0, 1, Bo, Ba, nullptr);
+            SWEEP(1, 1, Ba, Bb, nullptr);
+            SWEEP(2, 1, Bb, Ba, nullptr);
+            SWEEP(3, 1, Ba, Bb, nullptr);
+            SWEEP(4, -1, Bb, Ba, nullptr);
+            SWEEP(5, -1, Ba, Bb, nullptr);
+            SWEEP(6, -1, Bb, Ba, nullptr);
+            SWEEP(7, -1, Ba, Bb, Bo);
+#undef SWEEP
+            double e = block_max<NT>(err, red);
+            if (CL) {
+                // combine the partial maxima of the cluster's CTAs through global memory
+                if (threadIdx.x == 0) errPart[(long long)src * CS + rank] = e;
+                cooperative_groups::this_cluster().sync();
+                for (int q = 0; q < CS; q++) {
+                    const double eq = ((volatile double *)errPart)[(long long)src * CS + q];
+                    e = (e < eq) ? eq : e;
+                }
+                cooperative_groups::this_cluster().sync();
+            }
+            if (threadIdx.x == 0 && rank == 0 && errs) errs[(long long)src * max_rounds + r] = e;
             r++;
             // the result is in b; it becomes next round's "old"
             const int oo = o;
@@ -200,7 +256,7 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, double *__res
             b = oo;
             if (e < tol) { conv = true; break; }
         }
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && rank == 0) {
             if (rounds) rounds[src] = conv ? r : -r;
             where[src] = o;
         }
