@@ -103,3 +103,33 @@ def test_gloo_allreduce_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in ps]
     for p, o in zip(ps, outs):
         assert p.returncode == 0, o
+
+
+def test_lbfgs_driver_on_quadratic(lib, tmp_path, capsys):
+    """gpu_optimize (mirror of mpi_optimize's closure form): converges on a convex quadratic, logs like the
+    reference and checkpoints every `steps` gradient evaluations."""
+    rng = np.random.default_rng(0)
+    Q = rng.standard_normal((12, 12))
+    Q = Q @ Q.T + 12 * np.eye(12)
+    b = rng.standard_normal(12)
+    f = lambda x: 0.5 * x @ Q @ x - b @ x
+    g = lambda x: Q @ x - b
+    x, hist = lib.gpu_optimize(f, g, np.zeros(12), iterations=60, loc=str(tmp_path), steps=5)
+    assert np.abs(x - np.linalg.solve(Q, b)).max() < 1e-6
+    assert all(h2 <= h1 + 1e-12 for h1, h2 in zip(hist, hist[1:]))
+    out = capsys.readouterr().out
+    assert "iter 1, current loss=" in out and "================== STEP 1 ==================" in out
+    assert os.path.exists(tmp_path / "iter_5.npy")
+    with pytest.raises(ValueError):
+        lib.gpu_optimize(f, g, np.zeros(12), method="NelderMead")
+
+
+def test_box_filter_is_periodic_mean(lib):
+    a = np.random.default_rng(1).random((7, 6, 5))
+    s = lib.box_filter_periodic(a, 5, 3)
+    # brute force at one node with wrap-around indices
+    i, j, k = 0, 5, 4
+    ref = np.mean([a[(i + di) % 7, (j + dj) % 6, (k + dk) % 5] for di in range(-2, 3) for dj in range(-2, 3)
+                   for dk in range(-1, 2)])
+    assert s[i, j, k] == pytest.approx(ref, rel=1e-13)
+    assert s.sum() == pytest.approx(a.sum(), rel=1e-12)
