@@ -364,6 +364,10 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         pk = phase_begin(c, PH_FWD);
         if (cfg.CS > 1)
             rc = launch_fwd(c, k_fwd3d_v1<1024, 1, true>, 1024, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);
+        else if (c->fwd_variant == 2)
+            rc = launch_fwd(c, k_fwd3d_v1<768, 1, false>, 768, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);
+        else if (c->fwd_variant == 3)
+            rc = launch_fwd(c, k_fwd3d_v1<896, 1, false>, 896, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);
         else if (c->fwd_variant == 1)
             rc = launch_fwd(c, k_fwd3d_v1<1024, 2, false>, 1024, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);
         else
@@ -393,48 +397,39 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
 static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, const double *dG, const double *df,
                         double *dGU0, double *dGF, double *dGFsum, const Dims3 &d, double h, int S,
                         int *d_status) {
-    double *X;
+    double2 *UX, *GD;
     unsigned char *code, *cnt;
+    unsigned short *CM;
     int *Q, *cnts;   // cnts: [0,S) number of non-pinned nodes per source, [S,2S) ready-queue tails
     const size_t total = (size_t)S * d.N;
-    WS(c, "adj_x", double, total, X);
+    WS(c, "adj_ux", double2, total, UX);
+    WS(c, "adj_gd", double2, total, GD);
     WS(c, "adj_code", unsigned char, total, code);
+    WS(c, "adj_cm", unsigned short, total, CM);
     WS(c, "adj_cnt", unsigned char, (total + 7) & ~(size_t)3, cnt);
     WS(c, "adj_queue", int, total, Q);
     WS(c, "adj_counters", int, 3 * (size_t)S, cnts);
     CK(cudaMemsetAsync(cnts, 0, sizeof(int) * 3 * S, c->stream));
+    const dim3 eg(std::min(elem_grid(c, d.N), 128), S);
     int pk = phase_begin(c, PH_ADJ_SETUP);
-    k_adj3d_setup<<<dim3(std::min(elem_grid(c, d.N), 128), S), 256, 0, c->stream>>>(dU, dU0, dG, X, dGU0, code, cnts, d, S);
-    LAUNCHED(c, "k_adj3d_setup");
+    k_adj3d_setup2<<<eg, 256, 0, c->stream>>>(dU, dU0, dG, UX, GD, dGU0, code, cnts, d, S);
+    LAUNCHED(c, "k_adj3d_setup2");
     if (dGF || dGFsum) {
-        k_adj3d_count<<<dim3(std::min(elem_grid(c, d.N), 128), S), 256, 0, c->stream>>>(code, cnt, Q, cnts + S, d, S);
+        k_adj3d_count2<<<eg, 256, 0, c->stream>>>(code, CM, cnt, Q, cnts + S, d, S);
         phase_end(c, pk);
-        LAUNCHED(c, "k_adj3d_count");
-        // threads per source: as many as keep all sources of the batch resident at once
-        const char *ev = getenv("ADTOMO_ADJ_NT");
-        int nt = ev ? atoi(ev) : 0;
-        if (nt != 256 && nt != 512 && nt != 768 && nt != 1024) nt = 1024;   // measured best on the 256-source batch
-        auto launch = [&](auto kern, int NTv) -> int {
-            int occ = 1;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTv, 0));
-            if (occ < 1) occ = 1;
-            int grid = std::min(S, c->num_sms * occ);
-            kern<<<grid, NTv, 0, c->stream>>>(dU, dG, X, code, (unsigned int *)cnt, Q, cnts + S, cnts, d, S, d_status);
-            return 0;
-        };
+        LAUNCHED(c, "k_adj3d_count2");
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo2<1024>, 1024, 0));
+        if (occ < 1) occ = 1;
+        int grid = std::min(S, c->num_sms * occ);
         pk = phase_begin(c, PH_ADJ_SWEEP);
-        int lrc = 0;
-        if (nt == 256) lrc = launch(k_adj3d_topo<256>, 256);
-        else if (nt == 512) lrc = launch(k_adj3d_topo<512>, 512);
-        else if (nt == 768) lrc = launch(k_adj3d_topo<768>, 768);
-        else lrc = launch(k_adj3d_topo<1024>, 1024);
-        if (lrc) return lrc;
+        k_adj3d_topo2<1024><<<grid, 1024, 0, c->stream>>>(UX, GD, CM, (unsigned int *)cnt, Q, cnts + S, cnts, d, S, d_status);
         phase_end(c, pk);
-        LAUNCHED(c, "k_adj3d_topo");
+        LAUNCHED(c, "k_adj3d_topo2");
         pk = phase_begin(c, PH_ADJ_FINISH);
-        k_adj3d_finish<<<elem_grid(c, d.N), 256, 0, c->stream>>>(X, df, dGF, dGFsum, d.N, S, h);
+        k_adj3d_finish2<<<elem_grid(c, d.N), 256, 0, c->stream>>>(UX, df, dGF, dGFsum, d.N, S, h);
         phase_end(c, pk);
-        LAUNCHED(c, "k_adj3d_finish");
+        LAUNCHED(c, "k_adj3d_finish2");
     } else {
         phase_end(c, pk);
     }
@@ -554,7 +549,7 @@ extern "C" int adtomo_eikonal3d_backward_batch(adtomo_ctx *c, double *grad_u0, d
     if ((rc = stage_in(c, "f", f, (size_t)d.N, loc, &df))) return rc;
     int Sc = S;
     {
-        size_t per = sizeof(double) * (size_t)d.N * (loc == ADTOMO_HOST ? 6 : 1) + (size_t)d.N * 6;
+        size_t per = sizeof(double) * (size_t)d.N * (loc == ADTOMO_HOST ? 9 : 4) + (size_t)d.N * 8;
         size_t budget = free_bytes() / 2;
         Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
     }
@@ -804,7 +799,7 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     // per-source device footprint: U, U0, G, X (8 B each) + code (1 B)
     int Sc;
     {
-        size_t per = (size_t)d.N * (10 * sizeof(double) + 6);
+        size_t per = (size_t)d.N * (13 * sizeof(double) + 8);
         size_t budget = (size_t)(free_bytes() * 0.8);
         for (auto &kv : c->ws) budget += kv.second.second;   // what we already hold is reusable
         Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));

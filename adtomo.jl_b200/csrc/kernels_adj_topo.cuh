@@ -8,35 +8,88 @@
 // "ready" nodes wave by wave; every node is evaluated exactly once (O(N) work, independent of the
 // number of sweeps the forward solve needed), children are gathered in a fixed neighbour order,
 // so the result is deterministic.  One CTA per source; the ready queue lives in global memory.
+//
+// Data layout (the wavefront touches scattered nodes, so what counts is 32-byte sectors per node):
+//   UX  double2 {u, x}   a child contributes through ONE sector; x is stored next to the node's u
+//   GD  double2 {g, D}   right-hand side and diagonal, precomputed by the coalesced setup pass
+//   CM  uint16  low byte: parent side per axis + pinned flag (reference rules, tie -> +1);
+//               high byte: which of the 6 neighbours are children (no index arithmetic, no bounds
+//               checks and no neighbour-code reads in the wavefront)
+//   CNT uint8   children still pending (decremented with 32-bit atomics on the containing word)
 #pragma once
 #include "kernels_v0.cuh"
 
 namespace adtomo {
 
-// pass 2 of the setup: children counts and the initial ready set.  cnt is a byte per node;
-// pinned nodes get 0xFF so that decrements never make them "ready".
-__global__ void k_adj3d_count(const unsigned char *__restrict__ code, unsigned char *__restrict__ cnt,
-                              int *__restrict__ Q, int *__restrict__ qtail,
-                              const Dims3 d, const int S) {
+// pass 1 (coalesced): parent code, diagonal, interleaved copies, grad_u0.  grid = (blocks, S)
+__global__ void k_adj3d_setup2(const double *__restrict__ U, const double *__restrict__ U0,
+                               const double *__restrict__ G, double2 *__restrict__ UX, double2 *__restrict__ GD,
+                               double *__restrict__ GU0, unsigned char *__restrict__ code,
+                               int *__restrict__ remaining, const Dims3 d, const int S) {
+    const int src = blockIdx.y;
+    const long long base = (long long)src * d.N;
+    const double *u = U + base;
+    const int N = (int)d.N, n = d.n, l = d.l, nl = d.n * d.l;
+    int mycount = 0;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < N; id += gridDim.x * blockDim.x) {
+        const double ui = u[id];
+        const double gi = G[base + id];
+        const bool same = (ui == U0[base + id]);
+        if (GU0) GU0[base + id] = same ? gi : 0.0;       // Eikonal3D.cpp:106-110
+        unsigned cd;
+        double D = 0.0;
+        if (same) cd = ADJ_PIN | ADJ_DONE;
+        else {
+            const int i = id / nl;
+            const int r = id - i * nl;
+            const int j = r / l;
+            const int k = r - j * l;
+            const unsigned ci = adj_axis_code(u, id, i, d.m, nl, ui), cj = adj_axis_code(u, id, j, n, l, ui),
+                           ck = adj_axis_code(u, id, k, l, 1, ui);
+            cd = ci | (cj << 2) | (ck << 4);
+            if (cd == 0) cd = ADJ_PIN | ADJ_DONE;
+            else {
+                if (ci) D += 2.0 * (ui - u[ci == 1 ? id - nl : id + nl]);
+                if (cj) D += 2.0 * (ui - u[cj == 1 ? id - l : id + l]);
+                if (ck) D += 2.0 * (ui - u[ck == 1 ? id - 1 : id + 1]);
+            }
+        }
+        code[base + id] = (unsigned char)cd;
+        UX[base + id] = make_double2(ui, 0.0);
+        GD[base + id] = make_double2(gi, D);
+        if (!(cd & ADJ_DONE)) mycount++;
+    }
+    for (int o = 16; o > 0; o >>= 1) mycount += __shfl_xor_sync(0xffffffffu, mycount, o);
+    if ((threadIdx.x & 31) == 0 && mycount) atomicAdd(&remaining[src], mycount);
+}
+
+// pass 2 (coalesced): children mask + count, initial ready set.  Pinned nodes get count 0xFF so
+// that decrements never make them "ready".  grid = (blocks, S)
+__global__ void k_adj3d_count2(const unsigned char *__restrict__ code, unsigned short *__restrict__ CM,
+                               unsigned char *__restrict__ cnt, int *__restrict__ Q, int *__restrict__ qtail,
+                               const Dims3 d, const int S) {
     const int src = blockIdx.y;
     const long long base = (long long)src * d.N;
     const unsigned char *cd_ = code + base;
     const int N = (int)d.N, n = d.n, l = d.l, nl = d.n * d.l;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < N; id += gridDim.x * blockDim.x) {
         const unsigned cd = cd_[id];
-        if (cd & ADJ_PIN) { cnt[base + id] = 0xFF; continue; }
+        if (cd & ADJ_PIN) { cnt[base + id] = 0xFF; CM[base + id] = (unsigned short)cd; continue; }
         const int i = id / nl;
         const int r = id - i * nl;
         const int j = r / l;
         const int k = r - j * l;
-        int c = 0;
-        if (i > 0 && ((cd_[id - nl] >> 0) & 3u) == 2u) c++;
-        if (i < d.m - 1 && ((cd_[id + nl] >> 0) & 3u) == 1u) c++;
-        if (j > 0 && ((cd_[id - l] >> 2) & 3u) == 2u) c++;
-        if (j < n - 1 && ((cd_[id + l] >> 2) & 3u) == 1u) c++;
-        if (k > 0 && ((cd_[id - 1] >> 4) & 3u) == 2u) c++;
-        if (k < l - 1 && ((cd_[id + 1] >> 4) & 3u) == 1u) c++;
+        unsigned mask = 0;
+        // the -1 neighbour is my child iff its parent on this axis is its +1 side (2); the +1 neighbour iff 1
+        if (i > 0 && ((cd_[id - nl] >> 0) & 3u) == 2u) mask |= 1u;
+        if (i < d.m - 1 && ((cd_[id + nl] >> 0) & 3u) == 1u) mask |= 2u;
+        if (j > 0 && ((cd_[id - l] >> 2) & 3u) == 2u) mask |= 4u;
+        if (j < n - 1 && ((cd_[id + l] >> 2) & 3u) == 1u) mask |= 8u;
+        if (k > 0 && ((cd_[id - 1] >> 4) & 3u) == 2u) mask |= 16u;
+        if (k < l - 1 && ((cd_[id + 1] >> 4) & 3u) == 1u) mask |= 32u;
+        const int c = __popc(mask);
         cnt[base + id] = (unsigned char)c;
+        CM[base + id] = (unsigned short)(cd | (mask << 8));
         if (c == 0) {
             const int pos = atomicAdd(&qtail[src], 1);
             Q[base + pos] = id;
@@ -45,20 +98,19 @@ __global__ void k_adj3d_count(const unsigned char *__restrict__ code, unsigned c
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) k_adj3d_topo(const double *__restrict__ U, const double *__restrict__ G,
-                                                   double *X, const unsigned char *__restrict__ code,
-                                                   unsigned int *cnt32, int *Q, const int *__restrict__ qtail,
-                                                   const int *__restrict__ nfree, const Dims3 d, const int S,
-                                                   int *__restrict__ status) {
+__global__ void __launch_bounds__(NT) k_adj3d_topo2(double2 *UX, const double2 *__restrict__ GD,
+                                                    const unsigned short *__restrict__ CM, unsigned int *cnt32,
+                                                    int *Q, const int *__restrict__ qtail,
+                                                    const int *__restrict__ nfree, const Dims3 d, const int S,
+                                                    int *__restrict__ status) {
     __shared__ int s_tail;
-    const int m = d.m, n = d.n, l = d.l;
-    const long long si = (long long)n * l;
+    const int l = d.l;
+    const int nl = d.n * d.l;
     for (int src = blockIdx.x; src < S; src += gridDim.x) {
         const long long base = (long long)src * d.N;
-        const double *u = U + base;
-        const double *g = G + base;
-        double *x = X + base;
-        const unsigned char *cd_ = code + base;
+        double2 *ux = UX + base;
+        const double2 *gd = GD + base;
+        const unsigned short *cm_ = CM + base;
         int *q = Q + base;
         int head = 0, tail = qtail[src], waves = 0;
         if (threadIdx.x == 0) s_tail = tail;
@@ -66,36 +118,26 @@ __global__ void __launch_bounds__(NT) k_adj3d_topo(const double *__restrict__ U,
         while (head < tail) {
             for (int t = head + threadIdx.x; t < tail; t += NT) {
                 const int id = q[t];
-                const int k = id % l;
-                const int tt = id / l;
-                const int j = tt % n;
-                const int i = tt / n;
-                const unsigned cd = cd_[id];
-                const double ui = u[id];
+                const unsigned cm = cm_[id];
+                const double ui = ux[id].x;
+                const double2 g = gd[id];
                 double acc = 0.0;
-                // children, fixed order: i-1, i+1, j-1, j+1, k-1, k+1
-#define TOPO_CHILD(cond, off, shift, want)                                       \
-    if (cond) {                                                                  \
-        const unsigned cc = cd_[id + (off)];                                     \
-        if (((cc >> (shift)) & 3u) == (want)) acc += 2.0 * (u[id + (off)] - ui) * x[id + (off)]; \
+                // children in the fixed order i-1, i+1, j-1, j+1, k-1, k+1 (all final by construction)
+#define TOPO_CHILD(bit, off)                                        \
+    if (cm & ((bit) << 8)) {                                        \
+        const double2 c = ux[id + (off)];                           \
+        acc += 2.0 * (c.x - ui) * c.y;                              \
     }
-                TOPO_CHILD(i > 0, -si, 0, 2u)
-                TOPO_CHILD(i < m - 1, si, 0, 1u)
-                TOPO_CHILD(j > 0, -(long long)l, 2, 2u)
-                TOPO_CHILD(j < n - 1, (long long)l, 2, 1u)
-                TOPO_CHILD(k > 0, -1LL, 4, 2u)
-                TOPO_CHILD(k < l - 1, 1LL, 4, 1u)
+                TOPO_CHILD(1u, -nl)
+                TOPO_CHILD(2u, nl)
+                TOPO_CHILD(4u, -l)
+                TOPO_CHILD(8u, l)
+                TOPO_CHILD(16u, -1)
+                TOPO_CHILD(32u, 1)
 #undef TOPO_CHILD
-                const unsigned ci = cd & 3u, cj = (cd >> 2) & 3u, ck = (cd >> 4) & 3u;
-                const long long pi = ci == 1 ? id - si : id + si;
-                const long long pj = cj == 1 ? id - l : id + l;
-                const long long pk = ck == 1 ? id - 1 : id + 1;
-                double D = 0.0;
-                if (ci) D += 2.0 * (ui - u[pi]);
-                if (cj) D += 2.0 * (ui - u[pj]);
-                if (ck) D += 2.0 * (ui - u[pk]);
-                x[id] = (g[id] + acc) / D;
+                ux[id].y = (g.x + acc) / g.y;
                 // release the parents
+                const unsigned ci = cm & 3u, cj = (cm >> 2) & 3u, ck = (cm >> 4) & 3u;
 #define TOPO_RELEASE(active, p)                                                  \
     if (active) {                                                                \
         const long long gq = base + (p);                                         \
@@ -106,9 +148,9 @@ __global__ void __launch_bounds__(NT) k_adj3d_topo(const double *__restrict__ U,
             q[pos] = (int)(p);                                                   \
         }                                                                        \
     }
-                TOPO_RELEASE(ci, pi)
-                TOPO_RELEASE(cj, pj)
-                TOPO_RELEASE(ck, pk)
+                TOPO_RELEASE(ci, ci == 1 ? id - nl : id + nl)
+                TOPO_RELEASE(cj, cj == 1 ? id - l : id + l)
+                TOPO_RELEASE(ck, ck == 1 ? id - 1 : id + 1)
 #undef TOPO_RELEASE
             }
             __syncthreads();
@@ -120,6 +162,22 @@ __global__ void __launch_bounds__(NT) k_adj3d_topo(const double *__restrict__ U,
         }
         if (threadIdx.x == 0 && status) status[src] = (tail == nfree[src]) ? waves + 1 : -(waves + 1);
         __syncthreads();
+    }
+}
+
+// grad_f[s][q] = -x * (-2 f h h)  (Eikonal3D.cpp:113-116,194-196); optional sum over sources (fixed order).
+__global__ void k_adj3d_finish2(const double2 *__restrict__ UX, const double *__restrict__ f,
+                                double *__restrict__ GF, double *__restrict__ GFsum, const long long N, const int S,
+                                const double h) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (long long)gridDim.x * blockDim.x) {
+        const double rhs = -2 * f[q] * h * h;
+        double acc = 0.0;
+        for (int s = 0; s < S; s++) {
+            const double v = -UX[(long long)s * N + q].y * rhs;
+            if (GF) GF[(long long)s * N + q] = v;
+            acc += v;
+        }
+        if (GFsum) GFsum[q] = acc;
     }
 }
 
