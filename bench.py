@@ -108,7 +108,7 @@ def run_reference(args):
     w = workload(1, 0)
     cores = os.cpu_count() or 1
     procs = min(cores, 64)
-    n_src = procs                      # one source per worker process per step
+    n_src = 2 * procs                  # two sources per worker process per step
     times = []
     for it in range(args.warmup + args.steps):
         r = cpu_arm(w, n_src, procs)
@@ -124,7 +124,7 @@ def run_reference(args):
                                "512 receivers; CPU arm evaluates a bounded sample of the 256-source batch",
                    "sources_per_step": n_src},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": f"{n_src} of the 256 sources per step x {args.steps} steps, one source per worker "
+                         "sample": f"{n_src} of the 256 sources per step x {args.steps} steps, two sources per worker "
                                    f"process; oracle port of the reference sweeps, adjoint by back-substitution "
                                    f"(faster than the reference's Eigen SparseLU)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -266,7 +266,7 @@ def run_ours(args):
         return ms, ph / steps
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("ADTOMO_BENCH_NO_SMI"):
         sampler.start()
     ms_dev, phases = timed(step_device, args.steps, args.warmup)
     launches = int(timed.launches)
@@ -293,9 +293,15 @@ def run_ours(args):
             "misfit_ms": phases[1], "adjoint_setup_ms": phases[2], "finish_ms": phases[4], "layout_convert_ms": phases[5]}
     dom = "forward_sweeps" if fwd_ms >= adj_ms else "adjoint_sweeps"
     achieved = kern[dom]["gbs"]
+    # DRAM bytes of that kernel from the committed ncu --set full capture of this same launch (profiles/)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if dom == "forward_sweeps" and S == S_PER_GPU and (m, n, l) == GRID and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_gb_per_launch")
     step_alg_gbs = (bf + ba) / 1e6 / (ms_dev / args.steps)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write)",
+                "algorithmic_gb_per_launch": (bf if dom == "forward_sweeps" else ba) / 1e9, "peak_source": peak_src,
                 "whole_step_alg_gbs": step_alg_gbs, "whole_step_frac": step_alg_gbs / peak,
                 "note": "achieved = algorithmic bytes 8N(2+24K) fwd / 8N(6+24K) adj summed over the batch "
                         "(K = rounds each source ran) / CUDA-event time of that kernel on its launch stream"}
@@ -310,11 +316,11 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         procs = min(cores, 32)
-        n_src = min(S, procs)
+        n_src = min(S, 4 * procs)          # ~10-20 s of CPU work
         r = cpu_arm(w, n_src, procs)
         cpu = {"value": n_src / r["seconds"], "unit": UNIT, "cores": procs, "kind": "port",
-               "sample": f"first {n_src} of the {S} sources of this workload (forward+misfit+adjoint each), one per "
-                         f"worker process, {r['seconds']:.1f} s; oracle port, adjoint by back-substitution (faster "
+               "sample": f"first {n_src} of the {S} sources of this workload (forward+misfit+adjoint each) dealt to "
+                         f"{procs} worker processes, {r['seconds']:.1f} s; oracle port, adjoint by back-substitution (faster "
                          f"than the reference's SparseLU)",
                "rounds_match_gpu": bool(list(r["rounds"]) == list(rounds_dev[:n_src]))}
 
