@@ -15,6 +15,7 @@
 #include "kernels_v0.cuh"
 #include "kernels_adj_topo.cuh"
 #include "kernels_fwd_v1.cuh"
+#include "kernels_fwd_v2.cuh"
 
 using namespace adtomo;
 
@@ -283,7 +284,7 @@ static int get_plan(adtomo_ctx *c, int m, int n, int l, PlanCache **out) {
 
 // Shared-memory need of k_fwd3d_v1 when a source is split over a cluster of CS CTAs.
 struct FwdCfg { int CS; int sheet; int tOfSmem; size_t smem; };
-static bool fwd_config(const PlanCache *pc, int CS, FwdCfg *out) {
+static bool fwd_config(const PlanCache *pc, int CS, FwdCfg *out, int NS = 1) {
     int sheet = 0, ris = 0, fcLen = 0, tLen = 0;
     for (int q = 0; q < NLAYOUT; q++) {
         const LayoutDev &L = pc->dev.lay[q];
@@ -294,20 +295,22 @@ static bool fwd_config(const PlanCache *pc, int CS, FwdCfg *out) {
         fcLen = std::max(fcLen, L.dB + L.dC);
         tLen = std::max(tLen, L.dB * L.dC);
     }
-    size_t base = sizeof(double) * 2 * (size_t)sheet + sizeof(int) * ((size_t)NLAYOUT * ris + fcLen) + 16;
-    size_t withT = base + sizeof(unsigned short) * (size_t)tLen;
+    size_t base = sizeof(double) * 2 * NS * (size_t)sheet + sizeof(int) * ((size_t)NLAYOUT * ris + fcLen) + 16;
     if (base > SMEM_MAX_DYN) return false;
     out->CS = CS;
     out->sheet = sheet;
-    out->tOfSmem = withT <= SMEM_MAX_DYN;
-    out->smem = out->tOfSmem ? withT : base;
+    // packed-row table in shared memory: 8-bit when every row index fits a byte, else 16-bit, else global.
+    // (Shared memory is carved out of the 228 KB L1 in steps, so the smaller table also leaves more L1.)
+    if (fcLen - 2 <= 255 && base + (size_t)tLen <= SMEM_MAX_DYN) { out->tOfSmem = 2; out->smem = base + (size_t)tLen; }
+    else if (base + 2 * (size_t)tLen <= SMEM_MAX_DYN) { out->tOfSmem = 1; out->smem = base + 2 * (size_t)tLen; }
+    else { out->tOfSmem = 0; out->smem = base; }
     return true;
 }
 
 template <typename K>
 static int launch_fwd(adtomo_ctx *c, K kern, int NT, const FwdCfg &cfg, const PlanCache *pc, double *bufs,
                       const double *flay, double h, double tol, int max_rounds, int S, int *d_rounds, double *d_errs,
-                      int *where, double *errPart) {
+                      int *where, double *errPart, int NS = 1) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
     cudaLaunchConfig_t lc = {};
     lc.blockDim = dim3(NT);
@@ -315,7 +318,7 @@ static int launch_fwd(adtomo_ctx *c, K kern, int NT, const FwdCfg &cfg, const Pl
     lc.stream = c->stream;
     cudaLaunchAttribute at[1];
     int nattr = 0;
-    int nsrc = std::min(S, c->num_sms / cfg.CS);
+    int nsrc = std::min((S + NS - 1) / NS, c->num_sms / cfg.CS);   // concurrent source groups
     if (cfg.CS > 1) {
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = cfg.CS;
@@ -353,7 +356,7 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         WS(c, "fwd_bufs", double, (size_t)S * 3 * pc->dev.Mmax, bufs);
         WS(c, "fwd_flay", double, (size_t)NLAYOUT * pc->dev.Mmax, flay);
         WS(c, "fwd_where", int, S, where);
-        WS(c, "fwd_errpart", double, (size_t)S * 8, errPart);
+        WS(c, "fwd_errpart", double, (size_t)(S + 4) * 8, errPart);
         int pk = phase_begin(c, PH_CONVERT);
         const int eb = elem_grid(c, d.N);
         k_f_to_layouts<<<eb, 256, 0, c->stream>>>(pc->dev, df, flay);
@@ -362,7 +365,20 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         phase_end(c, pk);
         LAUNCHED(c, "k_u0_to_L0");
         pk = phase_begin(c, PH_FWD);
-        if (cfg.CS > 1)
+        // two sources per thread (shared index arithmetic): needs 4 sheets -> usually a cluster of 2
+        FwdCfg cfg2;
+        bool fits2 = false;
+        if (c->fwd_variant >= 10 && S >= 2)
+            for (int cs = 1; cs <= 8 && !fits2; cs *= 2) fits2 = fwd_config(pc, cs, &cfg2, 2);
+        if (fits2 && c->fwd_variant == 10 && cfg2.CS > 1)
+            rc = launch_fwd(c, k_fwd3d_v2<512, 2, true>, 512, cfg2, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart, 2);
+        else if (fits2 && c->fwd_variant == 10)
+            rc = launch_fwd(c, k_fwd3d_v2<512, 2, false>, 512, cfg2, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart, 2);
+        else if (fits2 && c->fwd_variant == 11 && cfg2.CS > 1)
+            rc = launch_fwd(c, k_fwd3d_v2<1024, 2, true>, 1024, cfg2, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart, 2);
+        else if (fits2 && c->fwd_variant == 11)
+            rc = launch_fwd(c, k_fwd3d_v2<1024, 2, false>, 1024, cfg2, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart, 2);
+        else if (cfg.CS > 1)
             rc = launch_fwd(c, k_fwd3d_v1<1024, 1, true>, 1024, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);
         else if (c->fwd_variant == 2)
             rc = launch_fwd(c, k_fwd3d_v1<768, 1, false>, 768, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);

@@ -42,8 +42,8 @@ template <int NT, int NPL, int DIR, bool CL>
 __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const double *rd, double *wr,
                                            const double *__restrict__ fl, const double *cmp, const double h,
                                            double *shA, double *shB, const int *ri, const int riStride,
-                                           int *fcS, const unsigned short *tOfS, const int rank, const int CS,
-                                           double &err) {
+                                           int *fcS, const unsigned short *tOfS, const int tOfMode, const int rank,
+                                           const int CS, double &err) {
     const SweepDev W = P.sw[sw];
     const LayoutDev &L = P.lay[W.rl];
     const LayoutDev &X = P.lay[W.wl];
@@ -61,9 +61,14 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
     const int nown = a1 - a0;
     // tables of this layout (tOf stays in global memory when it does not fit: tOfS == nullptr)
     for (int q = threadIdx.x; q < T + 2; q += NT) fcS[q] = L.fcum[q];
-    const unsigned short *tOfT = tOfS ? tOfS : L.tOf;
-    if (tOfS)
+    // packed-row table: 8-bit copy in shared memory when every t fits a byte (tOfMode 2), 16-bit copy
+    // (1), or the global table (0)
+    const unsigned short *tOfT = tOfMode == 1 ? tOfS : L.tOf;
+    unsigned char *tOf8 = (unsigned char *)tOfS;
+    if (tOfMode == 1)
         for (int q = threadIdx.x; q < dB * dC; q += NT) ((unsigned short *)tOfS)[q] = L.tOf[q];
+    if (tOfMode == 2)
+        for (int q = threadIdx.x; q < dB * dC; q += NT) tOf8[q] = (unsigned char)L.tOf[q];
     // +inf borders/halos for this layout's sheet geometry
     for (int q = threadIdx.x; q < pitch; q += NT) {
         shA[q] = EIK_INF; shB[q] = EIK_INF;
@@ -121,7 +126,7 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
                 A_[k] = 0; B_[k] = 0; C_[k] = 0;
                 if (valid[k]) {
                     const int e = q0 + q;
-                    const int t = tOfT[e];
+                    const int t = tOfMode == 2 ? (int)tOf8[e] : (int)tOfT[e];
                     const int B = max(0, t - (dC - 1)) + (e - fcS[t]);
                     const int A = lam - t, C = t - B;
                     A_[k] = A; B_[k] = B; C_[k] = C;
@@ -213,6 +218,7 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, const int she
     int fcLen = 0;
     for (int q = 0; q < NLAYOUT; q++) fcLen = max(fcLen, P.lay[q].dB + P.lay[q].dC);
     unsigned short *tOfS = tOfSmem ? (unsigned short *)(fcS + fcLen) : nullptr;
+    const int tOfMode = tOfSmem;
     for (int q = 0; q < NLAYOUT; q++)
         for (int t = threadIdx.x; t <= P.lay[q].nlev; t += NT) ri[q * riStride + t] = P.lay[q].rowIndex[t];
     __syncthreads();
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, const int she
             double err = 0.0;
             double *Bo = B3 + o * N, *Ba = B3 + a * N, *Bb = B3 + b * N;
 #define SWEEP(k, D, RD, WR, CMP) \
-    sweep3d_v1<NT, NPL, D, CL>(P, k, RD, WR, flay + (long long)P.sw[k].rl * MF, CMP, h, shA, shB, ri, riStride, fcS, tOfS, rank, CS, err)
+    sweep3d_v1<NT, NPL, D, CL>(P, k, RD, WR, flay + (long long)P.sw[k].rl * MF, CMP, h, shA, shB, ri, riStride, fcS, tOfS, tOfMode, rank, CS, err)
             SWEEP(0, 1, Bo, Ba, nullptr);
             SWEEP(1, 1, Ba, Bb, nullptr);
             SWEEP(2, 1, Bb, Ba, nullptr);
