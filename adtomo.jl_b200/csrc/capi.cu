@@ -192,6 +192,12 @@ extern "C" double adtomo_last_phase_ms(adtomo_ctx *c, int phase) {
     return tot;
 }
 
+extern "C" int adtomo_debug_set_progress(void *host_mapped_ints) {
+    int *p = (int *)host_mapped_ints;
+    cudaError_t e = cudaMemcpyToSymbol(g_dbg_progress, &p, sizeof(p));
+    return e == cudaSuccess ? 0 : -2;
+}
+
 static adtomo_ctx *default_ctx(int *rc) {
     static thread_local adtomo_ctx *c = nullptr;
     *rc = 0;
@@ -283,7 +289,7 @@ static int get_plan(adtomo_ctx *c, int m, int n, int l, PlanCache **out) {
 }
 
 // Shared-memory need of k_fwd3d_v1 when a source is split over a cluster of CS CTAs.
-struct FwdCfg { int CS; int sheet; int tOfSmem; size_t smem; };
+struct FwdCfg { int CS; int sheet; int tOfSmem; int barsOffset; size_t smem; };
 static bool fwd_config(const PlanCache *pc, int CS, FwdCfg *out, int NS = 1) {
     int sheet = 0, ris = 0, fcLen = 0, tLen = 0;
     for (int q = 0; q < NLAYOUT; q++) {
@@ -304,14 +310,16 @@ static bool fwd_config(const PlanCache *pc, int CS, FwdCfg *out, int NS = 1) {
     if (fcLen - 2 <= 255 && base + (size_t)tLen <= SMEM_MAX_DYN) { out->tOfSmem = 2; out->smem = base + (size_t)tLen; }
     else if (base + 2 * (size_t)tLen <= SMEM_MAX_DYN) { out->tOfSmem = 1; out->smem = base + 2 * (size_t)tLen; }
     else { out->tOfSmem = 0; out->smem = base; }
-    return true;
+    out->barsOffset = (int)((out->smem + 7) & ~(size_t)7);   // 4 mbarriers for the cluster halo exchange
+    out->smem = out->barsOffset + 64;
+    return out->smem <= SMEM_MAX_DYN + 128;
 }
 
 template <typename K>
 static int launch_fwd(adtomo_ctx *c, K kern, int NT, const FwdCfg &cfg, const PlanCache *pc, double *bufs,
                       const double *flay, double h, double tol, int max_rounds, int S, int *d_rounds, double *d_errs,
                       int *where, double *errPart, int NS = 1) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX_DYN + 128));
     cudaLaunchConfig_t lc = {};
     lc.blockDim = dim3(NT);
     lc.dynamicSmemBytes = cfg.smem;
@@ -335,7 +343,7 @@ static int launch_fwd(adtomo_ctx *c, K kern, int NT, const FwdCfg &cfg, const Pl
     lc.gridDim = dim3(cfg.CS * nsrc);
     lc.attrs = nattr ? at : nullptr;
     lc.numAttrs = nattr;
-    CK(cudaLaunchKernelEx(&lc, kern, pc->dev, cfg.sheet, cfg.tOfSmem, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs,
+    CK(cudaLaunchKernelEx(&lc, kern, pc->dev, cfg.sheet, cfg.tOfSmem, cfg.barsOffset, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs,
                           where, errPart));
     return 0;
 }

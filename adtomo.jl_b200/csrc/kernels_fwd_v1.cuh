@@ -20,8 +20,11 @@
 #include <cooperative_groups.h>
 #include "kernels_v0.cuh"
 #include "layouts.h"
+#include "cluster_halo.cuh"
 
 namespace adtomo {
+
+__device__ volatile int *g_dbg_progress = nullptr;   // debugging aid (host-mapped memory), see adtomo_debug_set_progress
 
 #define EIK_INF __longlong_as_double(0x7ff0000000000000LL)
 
@@ -43,7 +46,7 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
                                            const double *__restrict__ fl, const double *cmp, const double h,
                                            double *shA, double *shB, const int *ri, const int riStride,
                                            int *fcS, const unsigned short *tOfS, const int tOfMode, const int rank,
-                                           const int CS, double &err) {
+                                           const int CS, uint64_t *bars, double &err) {
     const SweepDev W = P.sw[sw];
     const LayoutDev &L = P.lay[W.rl];
     const LayoutDev &X = P.lay[W.wl];
@@ -78,30 +81,66 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
         shA[q * pitch] = EIK_INF; shB[q * pitch] = EIK_INF;
         shA[q * pitch + dB + 1] = EIK_INF; shB[q * pitch + dB + 1] = EIK_INF;
     }
-    double *rmA = nullptr, *rmB = nullptr;   // neighbour's sheets (the one downstream in this sweep's direction)
-    int rmRow = 0;                           // halo row of the neighbour that mirrors my boundary row
-    const int myEdge = DIR > 0 ? a1 - 1 : a0;
-    bool push = false;
+    // cluster mode: halo exchange with the neighbours (cluster_halo.cuh).  "up" pushes its edge row into
+    // my halo, I push my edge row into "down"'s halo.
+    const int myEdge = DIR > 0 ? a1 - 1 : a0;          // my row that the downstream neighbour needs
+    bool hasUp = false, hasDown = false;
+    unsigned rmFull[2] = {0, 0}, rmEmpty[2] = {0, 0}, rmSheet[2] = {0, 0};
+    unsigned phFull[2] = {0, 0}, phEmpty[2] = {0, 0};
     if (CL) {
-        namespace cg = cooperative_groups;
-        cg::cluster_group cluster = cg::this_cluster();
-        const int nb = rank + DIR;
-        if (nb >= 0 && nb < CS) {
-            push = true;
-            rmA = cluster.map_shared_rank(shA, nb);
-            rmB = cluster.map_shared_rank(shB, nb);
-            const int nb0 = (dA * nb) / CS, nb1 = (dA * (nb + 1)) / CS;
-            rmRow = DIR > 0 ? 0 : (nb1 - nb0 + 1);
+        const int up = rank - DIR, down = rank + DIR;
+        hasUp = up >= 0 && up < CS;
+        hasDown = down >= 0 && down < CS;
+        if (threadIdx.x == 0) {
+            for (int q = 0; q < 4; q++) mbar_init(&bars[q], 1);
+            mbar_init_fence();
         }
-        cluster.sync();
+        if (hasDown) {
+            const int nb0 = (dA * down) / CS, nb1 = (dA * (down + 1)) / CS;
+            const int rmRow = DIR > 0 ? 0 : (nb1 - nb0 + 1);
+            rmFull[0] = cluster_map(smem_u32(&bars[0]), down);
+            rmFull[1] = cluster_map(smem_u32(&bars[1]), down);
+            rmSheet[0] = cluster_map(smem_u32(shA), down) + (unsigned)(rmRow * pitch + 1) * 8u;
+            rmSheet[1] = cluster_map(smem_u32(shB), down) + (unsigned)(rmRow * pitch + 1) * 8u;
+        }
+        if (hasUp) {
+            rmEmpty[0] = cluster_map(smem_u32(&bars[2]), up);
+            rmEmpty[1] = cluster_map(smem_u32(&bars[3]), up);
+        }
+        cooperative_groups::this_cluster().sync();   // once per sweep: barrier init + previous sweep's global writes
     } else {
         __syncthreads();
     }
-    double *shPrev = shA, *shCur = shB;
-    double *rmCur = rmB;
     for (int step = 0; step < nlev; step++) {
         const int lam = dir > 0 ? step : nlev - 1 - step;
         const int Alo = max(0, lam - T), Ahi = min(dA - 1, lam);
+        const int p = step & 1;                       // sheet buffer written at this step
+        if (CL && g_dbg_progress && threadIdx.x == 0 && blockIdx.x < 8) {
+            g_dbg_progress[blockIdx.x * 4 + 0] = sw;
+            g_dbg_progress[blockIdx.x * 4 + 1] = step;
+            g_dbg_progress[blockIdx.x * 4 + 2] = 1;
+        }
+        double *shCur = p ? shB : shA;
+        const double *shPrev = p ? shA : shB;
+        bool pushing = false;
+        if (CL) {
+            // ONE thread talks to the mbarriers (several waiters could miss a phase: the neighbour may
+            // arrive again as soon as thread 0 has signalled); the CTA barrier below releases the others.
+            pushing = hasDown && step <= nlev - 2;
+            if (threadIdx.x == 0) {
+                if (hasUp && step >= 1) mbar_wait(&bars[1 - p], phFull[1 - p]);      // halo of step-1 has landed
+                if (pushing && step >= 2) mbar_wait(&bars[2 + p], phEmpty[p]);       // neighbour done with buffer p
+                if (pushing) {
+                    const int t = lam - myEdge;
+                    const unsigned len = (myEdge >= Alo && myEdge <= Ahi) ? (unsigned)(fcS[t + 1] - fcS[t]) : 0u;
+                    mbar_remote_arrive_tx(rmFull[p], len * 8u);                         // announce this step's push
+                }
+            }
+            if (hasUp && step >= 1) phFull[1 - p] ^= 1u;
+            if (pushing && step >= 2) phEmpty[p] ^= 1u;
+            __syncthreads();
+        }
+        if (CL && g_dbg_progress && threadIdx.x == 0 && blockIdx.x < 8) g_dbg_progress[blockIdx.x * 4 + 2] = 2;
         const int Amin = max(Alo, a0), Amax = min(Ahi, a1 - 1);   // my rows in this level
         const int q0 = Amax >= Amin ? fcS[lam - Amax] : 0;        // packed index of my first node
         const int cnt = Amax >= Amin ? fcS[lam - Amin + 1] - q0 : 0;
@@ -167,7 +206,7 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
                 if (valid[k]) {
                     const int A = A_[k], B = B_[k], C = C_[k];
                     shCur[(A - a0 + 1) * pitch + B + 1] = res[k];
-                    if (CL && push && A == myEdge) rmCur[rmRow * pitch + B + 1] = res[k];   // DSMEM halo push
+                    if (CL && pushing && A == myEdge) st_async_f64(rmSheet[p] + (unsigned)B * 8u, res[k], rmFull[p]);   // DSMEM halo push
                     // position in the next sweep's layout
                     const int cv = W.vi == 0 ? A : (W.vi == 1 ? B : C);
                     const int ct = W.ti == 0 ? A : (W.ti == 1 ? B : C);
@@ -182,12 +221,9 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
                 }
             }
         }
-        if (CL) cooperative_groups::this_cluster().sync();
-        else __syncthreads();
-        double *tmp = shPrev;
-        shPrev = shCur;
-        shCur = tmp;
-        rmCur = (rmCur == rmB) ? rmA : rmB;
+        __syncthreads();
+        // tell the upstream neighbour that its next push into buffer 1-p may proceed
+        if (CL && hasUp && step >= 1 && step <= nlev - 3 && threadIdx.x == 0) mbar_remote_arrive(rmEmpty[1 - p]);
     }
 }
 
@@ -197,6 +233,7 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
 // CL: launched with a cluster of CS = cluster size CTAs per source; errPart: S*CS doubles.
 template <int NT, int NPL, bool CL>
 __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, const int sheet, const int tOfSmem,
+                                                    const int barsOffset,
                                                     double *__restrict__ bufs, const double *__restrict__ flay,
                                                     const double h, const double tol, const int max_rounds,
                                                     const int S, int *__restrict__ rounds,
@@ -219,6 +256,7 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, const int she
     for (int q = 0; q < NLAYOUT; q++) fcLen = max(fcLen, P.lay[q].dB + P.lay[q].dC);
     unsigned short *tOfS = tOfSmem ? (unsigned short *)(fcS + fcLen) : nullptr;
     const int tOfMode = tOfSmem;
+    uint64_t *bars = (uint64_t *)((char *)sheets + barsOffset);   // 4 mbarriers, 8-byte aligned (host computes the offset)
     for (int q = 0; q < NLAYOUT; q++)
         for (int t = threadIdx.x; t <= P.lay[q].nlev; t += NT) ri[q * riStride + t] = P.lay[q].rowIndex[t];
     __syncthreads();
@@ -233,7 +271,7 @@ __global__ void __launch_bounds__(NT, 1) k_fwd3d_v1(const Plan3 P, const int she
             double err = 0.0;
             double *Bo = B3 + o * N, *Ba = B3 + a * N, *Bb = B3 + b * N;
 #define SWEEP(k, D, RD, WR, CMP) \
-    sweep3d_v1<NT, NPL, D, CL>(P, k, RD, WR, flay + (long long)P.sw[k].rl * MF, CMP, h, shA, shB, ri, riStride, fcS, tOfS, tOfMode, rank, CS, err)
+    sweep3d_v1<NT, NPL, D, CL>(P, k, RD, WR, flay + (long long)P.sw[k].rl * MF, CMP, h, shA, shB, ri, riStride, fcS, tOfS, tOfMode, rank, CS, bars, err)
             SWEEP(0, 1, Bo, Ba, nullptr);
             SWEEP(1, 1, Ba, Bb, nullptr);
             SWEEP(2, 1, Bb, Ba, nullptr);

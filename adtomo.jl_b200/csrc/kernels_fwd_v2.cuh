@@ -162,6 +162,7 @@ __device__ __forceinline__ void sweep3d_v2(const Plan3 &P, const int sw, const d
 // Groups of NS consecutive sources are processed together by one cluster (CL) or one CTA.
 template <int NT, int NS, bool CL>
 __global__ void __launch_bounds__(NT, 1) k_fwd3d_v2(const Plan3 P, const int sheet, const int tOfSmem,
+                                                    const int barsOffset,
                                                     double *__restrict__ bufs, const double *__restrict__ flay,
                                                     const double h, const double tol, const int max_rounds,
                                                     const int S, int *__restrict__ rounds,
