@@ -15,7 +15,6 @@
 #include "kernels_v0.cuh"
 #include "kernels_adj_topo.cuh"
 #include "kernels_fwd_v1.cuh"
-#include "kernels_fwd_v2.cuh"
 
 using namespace adtomo;
 
@@ -190,12 +189,6 @@ extern "C" double adtomo_last_phase_ms(adtomo_ctx *c, int phase) {
         else cudaGetLastError();
     }
     return tot;
-}
-
-extern "C" int adtomo_debug_set_progress(void *host_mapped_ints) {
-    int *p = (int *)host_mapped_ints;
-    cudaError_t e = cudaMemcpyToSymbol(g_dbg_progress, &p, sizeof(p));
-    return e == cudaSuccess ? 0 : -2;
 }
 
 static adtomo_ctx *default_ctx(int *rc) {
@@ -373,20 +366,7 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         phase_end(c, pk);
         LAUNCHED(c, "k_u0_to_L0");
         pk = phase_begin(c, PH_FWD);
-        // two sources per thread (shared index arithmetic): needs 4 sheets -> usually a cluster of 2
-        FwdCfg cfg2;
-        bool fits2 = false;
-        if (c->fwd_variant >= 10 && S >= 2)
-            for (int cs = 1; cs <= 8 && !fits2; cs *= 2) fits2 = fwd_config(pc, cs, &cfg2, 2);
-        if (fits2 && c->fwd_variant == 10 && cfg2.CS > 1)
-            rc = launch_fwd(c, k_fwd3d_v2<512, 2, true>, 512, cfg2, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart, 2);
-        else if (fits2 && c->fwd_variant == 10)
-            rc = launch_fwd(c, k_fwd3d_v2<512, 2, false>, 512, cfg2, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart, 2);
-        else if (fits2 && c->fwd_variant == 11 && cfg2.CS > 1)
-            rc = launch_fwd(c, k_fwd3d_v2<1024, 2, true>, 1024, cfg2, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart, 2);
-        else if (fits2 && c->fwd_variant == 11)
-            rc = launch_fwd(c, k_fwd3d_v2<1024, 2, false>, 1024, cfg2, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart, 2);
-        else if (cfg.CS > 1)
+        if (cfg.CS > 1)
             rc = launch_fwd(c, k_fwd3d_v1<1024, 1, true>, 1024, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);
         else if (c->fwd_variant == 2)
             rc = launch_fwd(c, k_fwd3d_v1<768, 1, false>, 768, cfg, pc, bufs, flay, h, tol, max_rounds, S, d_rounds, d_errs, where, errPart);

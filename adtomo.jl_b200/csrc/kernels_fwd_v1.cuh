@@ -24,8 +24,6 @@
 
 namespace adtomo {
 
-__device__ volatile int *g_dbg_progress = nullptr;   // debugging aid (host-mapped memory), see adtomo_debug_set_progress
-
 #define EIK_INF __longlong_as_double(0x7ff0000000000000LL)
 
 // One directional sweep.  shA/shB: two (dA+2) x pitch sheets with a +inf border (a missing upwind
@@ -115,11 +113,6 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
         const int lam = dir > 0 ? step : nlev - 1 - step;
         const int Alo = max(0, lam - T), Ahi = min(dA - 1, lam);
         const int p = step & 1;                       // sheet buffer written at this step
-        if (CL && g_dbg_progress && threadIdx.x == 0 && blockIdx.x < 8) {
-            g_dbg_progress[blockIdx.x * 4 + 0] = sw;
-            g_dbg_progress[blockIdx.x * 4 + 1] = step;
-            g_dbg_progress[blockIdx.x * 4 + 2] = 1;
-        }
         double *shCur = p ? shB : shA;
         const double *shPrev = p ? shA : shB;
         bool pushing = false;
@@ -140,7 +133,6 @@ __device__ __forceinline__ void sweep3d_v1(const Plan3 &P, const int sw, const d
             if (pushing && step >= 2) phEmpty[p] ^= 1u;
             __syncthreads();
         }
-        if (CL && g_dbg_progress && threadIdx.x == 0 && blockIdx.x < 8) g_dbg_progress[blockIdx.x * 4 + 2] = 2;
         const int Amin = max(Alo, a0), Amax = min(Ahi, a1 - 1);   // my rows in this level
         const int q0 = Amax >= Amin ? fcS[lam - Amax] : 0;        // packed index of my first node
         const int cnt = Amax >= Amin ? fcS[lam - Amin + 1] - q0 : 0;

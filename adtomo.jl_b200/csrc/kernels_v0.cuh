@@ -1,6 +1,9 @@
-// kernels_v0.cuh -- first correct CUDA path (round 1, step 1): one CTA per source, hyperplane
-// (level-set) ordering of every directional Gauss-Seidel sweep, fields in the reference's
-// row-major layout in global memory.
+// kernels_v0.cuh -- shared device helpers, the row-major FALLBACK 3D forward kernel (grids whose
+// sheets do not fit the level-major kernel), the fused-step helpers (sparse sources, receiver
+// sampling, misfit) and the 2D kernels.
+//
+// k_fwd3d_v0: one CTA per source, hyperplane (level-set) ordering of every directional Gauss-Seidel
+// sweep, fields in the reference's row-major layout in global memory.
 //
 // Why hyperplanes: in a sweep with directions (di,dj,dk) node (I,J,K) (sweep coordinates, i.e.
 // reflected so that the sweep ascends) reads the NEW values of (I-1,J,K),(I,J-1,K),(I,J,K-1)
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(NT) k_fwd3d_v0(double *__restrict__ U, double 
 }
 
 // ------------------------------------------------------------------------------------------
-// 3D adjoint, v0.  code byte per node: bits [2a,2a+1] for axis a in {i,j,k}: 0 = axis inactive,
+// adjoint parent code (shared by the 3D wavefront kernels and the 2D kernel).  code byte per node: bits [2a,2a+1] for axis a in {i,j,k}: 0 = axis inactive,
 // 1 = upwind parent is the -1 neighbour, 2 = parent is the +1 neighbour; bit 6 = value final;
 // bit 7 = pinned (row of Z in Eikonal3D.cpp:126-130,168-171: x = 0).
 // ------------------------------------------------------------------------------------------
@@ -141,142 +144,6 @@ __device__ __forceinline__ unsigned adj_axis_code(const double *u, long long id,
     else side = (u[id + stride] > u[id - stride]) ? 1 : 2;
     const double a = side == 1 ? u[id - stride] : u[id + stride];
     return (ui > a) ? (unsigned)side : 0u;
-}
-
-// Elementwise; grid = (blocks, S): 32-bit index math only (64-bit div/mod dominated the first version).
-__global__ void k_adj3d_setup(const double *__restrict__ U, const double *__restrict__ U0,
-                              const double *__restrict__ G, double *__restrict__ X, double *__restrict__ GU0,
-                              unsigned char *__restrict__ code, int *__restrict__ remaining, const Dims3 d,
-                              const int S) {
-    const int src = blockIdx.y;
-    const long long base = (long long)src * d.N;
-    const double *u = U + base;
-    const int N = (int)d.N, n = d.n, l = d.l, nl = d.n * d.l;
-    int mycount = 0;
-    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < N; id += gridDim.x * blockDim.x) {
-        const double ui = u[id];
-        const bool same = (ui == U0[base + id]);
-        if (GU0) GU0[base + id] = same ? G[base + id] : 0.0;
-        unsigned cd;
-        if (same) cd = ADJ_PIN | ADJ_DONE;
-        else {
-            const int i = id / nl;
-            const int r = id - i * nl;
-            const int j = r / l;
-            const int k = r - j * l;
-            cd = adj_axis_code(u, id, i, d.m, nl, ui) | (adj_axis_code(u, id, j, n, l, ui) << 2) |
-                 (adj_axis_code(u, id, k, l, 1, ui) << 4);
-            if (cd == 0) cd = ADJ_PIN | ADJ_DONE;
-        }
-        code[base + id] = (unsigned char)cd;
-        X[base + id] = 0.0;
-        if (!(cd & ADJ_DONE)) mycount++;
-    }
-    for (int o = 16; o > 0; o >>= 1) mycount += __shfl_xor_sync(0xffffffffu, mycount, o);
-    if ((threadIdx.x & 31) == 0 && mycount) atomicAdd(&remaining[src], mycount);
-}
-
-template <int NT>
-__device__ int adj_sweep3d_v0(const double *__restrict__ u, const double *__restrict__ g, double *x,
-                              unsigned char *code, const Dims3 d, const int di, const int dj, const int dk) {
-    const int m = d.m, n = d.n, l = d.l;
-    const int nlev = m + n + l - 2;
-    const long long si = (long long)n * l;
-    int fin = 0;
-    for (int s = 0; s < nlev; s++) {
-        const int Jlo = max(0, s - (m - 1) - (l - 1));
-        const int Jhi = min(n - 1, s);
-        const int cnt = (Jhi - Jlo + 1) * l;
-        for (int idx = threadIdx.x; idx < cnt; idx += NT) {
-            const int Jr = idx / l;
-            const int K = idx - Jr * l;
-            const int J = Jlo + Jr;
-            const int I = s - J - K;
-            if (I < 0 || I >= m) continue;
-            const int i = di > 0 ? I : m - 1 - I;
-            const int j = dj > 0 ? J : n - 1 - J;
-            const int k = dk > 0 ? K : l - 1 - K;
-            const long long id = ((long long)i * n + j) * l + k;
-            const unsigned cd = code[id];
-            if (cd & ADJ_DONE) continue;
-            const double ui = u[id];
-            double acc = 0.0;
-            bool ok = true;
-            // children: the -1 neighbour c is my child iff its parent on this axis is its +1 side (2);
-            //           the +1 neighbour c is my child iff its parent is its -1 side (1).
-#define ADJ_CHILD(cond, off, shift, want)                                            \
-    if (cond) {                                                                      \
-        const unsigned cc = code[id + (off)];                                        \
-        if (((cc >> (shift)) & 3u) == (want)) {                                      \
-            if (!(cc & ADJ_DONE)) ok = false;                                        \
-            else acc += 2.0 * (u[id + (off)] - ui) * x[id + (off)];                  \
-        }                                                                            \
-    }
-            ADJ_CHILD(i > 0, -si, 0, 2u)
-            ADJ_CHILD(i < m - 1, si, 0, 1u)
-            ADJ_CHILD(j > 0, -(long long)l, 2, 2u)
-            ADJ_CHILD(j < n - 1, (long long)l, 2, 1u)
-            ADJ_CHILD(k > 0, -1LL, 4, 2u)
-            ADJ_CHILD(k < l - 1, 1LL, 4, 1u)
-#undef ADJ_CHILD
-            if (!ok) continue;
-            double D = 0.0;
-            const unsigned ci = cd & 3u, cj = (cd >> 2) & 3u, ck = (cd >> 4) & 3u;
-            if (ci) D += 2.0 * (ui - u[ci == 1 ? id - si : id + si]);
-            if (cj) D += 2.0 * (ui - u[cj == 1 ? id - l : id + l]);
-            if (ck) D += 2.0 * (ui - u[ck == 1 ? id - 1 : id + 1]);
-            x[id] = (g[id] + acc) / D;
-            code[id] = (unsigned char)(cd | ADJ_DONE);
-            fin++;
-        }
-        __syncthreads();
-    }
-    return fin;
-}
-
-// One CTA per source.  status[src]: sweeps used (>0) or -(sweeps) if the solve stalled.
-template <int NT>
-__global__ void __launch_bounds__(NT) k_adj3d_v0(const double *__restrict__ U, const double *__restrict__ G,
-                                                 double *__restrict__ X, unsigned char *__restrict__ code,
-                                                 int *__restrict__ remaining, const Dims3 d, const int S,
-                                                 const int max_rounds, int *__restrict__ status) {
-    __shared__ int red[NT / 32];
-    for (int src = blockIdx.x; src < S; src += gridDim.x) {
-        const long long off = (long long)src * d.N;
-        int rem = remaining[src];
-        int sweeps = 0;
-        bool stalled = false;
-        // adjoint information flows from large to small travel time: run the round backwards
-        for (int r = 0; r < max_rounds && rem > 0 && !stalled; r++) {
-            int round_fin = 0;
-            for (int sw = 7; sw >= 0 && rem > 0; sw--) {
-                int fin = adj_sweep3d_v0<NT>(U + off, G + off, X + off, code + off, d, -c_dirs3[sw][0],
-                                             -c_dirs3[sw][1], -c_dirs3[sw][2]);
-                fin = block_sum_int<NT>(fin, red);
-                rem -= fin;
-                round_fin += fin;
-                sweeps++;
-            }
-            if (round_fin == 0) stalled = true;
-        }
-        if (threadIdx.x == 0 && status) status[src] = (rem > 0) ? -sweeps : sweeps;
-        __syncthreads();
-    }
-}
-
-// grad_f[s][q] = -x * (-2 f h h)  (Eikonal3D.cpp:113-116,194-196); optional sum over sources.
-__global__ void k_adj3d_finish(const double *__restrict__ X, const double *__restrict__ f, double *__restrict__ GF,
-                               double *__restrict__ GFsum, const long long N, const int S, const double h) {
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (long long)gridDim.x * blockDim.x) {
-        const double rhs = -2 * f[q] * h * h;
-        double acc = 0.0;
-        for (int s = 0; s < S; s++) {
-            const double v = -X[(long long)s * N + q] * rhs;
-            if (GF) GF[(long long)s * N + q] = v;
-            acc += v;
-        }
-        if (GFsum) GFsum[q] = acc;
-    }
 }
 
 // ------------------------------------------------------------------------------------------
