@@ -245,7 +245,7 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
-        for _ in range(warmup):
+        for _ in range(max(warmup, 3) + 1):     # >= 3 warm-up steps (+1: first-touch of workspaces and clocks settle)
             fn()
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -273,7 +273,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     rounds_dev = rounds.copy()
     mis_dev = float(d_packed[N].item())
-    ms_e2e, _ = timed(step_host, args.steps, max(1, args.warmup // 2) if args.warmup else 0)
+    ms_e2e, _ = timed(step_host, args.steps, args.warmup)
     mis_e2e = float(h_packed[N].item())
 
     total_sources = S * world
