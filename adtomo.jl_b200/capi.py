@@ -90,6 +90,14 @@ def load_library():
     L.adtomo_eikonal3d_misfit_grad.restype = c_int
     L.adtomo_eikonal3d_misfit_grad.argtypes = [_vp, _vp, _vp, _vp, c_double, c_int, c_int, c_int, c_double, c_int,
                                                c_int, _vp, _vp, _vp, c_double, c_int, _vp, _vp, _vp, _vp, c_int]
+    L.adtomo_nccl_unique_id.restype = c_int
+    L.adtomo_nccl_unique_id.argtypes = [ctypes.c_char_p]
+    L.adtomo_nccl_init.restype = c_int
+    L.adtomo_nccl_init.argtypes = [_vp, ctypes.c_char_p, c_int, c_int]
+    L.adtomo_nccl_allreduce_sum.restype = c_int
+    L.adtomo_nccl_allreduce_sum.argtypes = [_vp, _vp, ctypes.c_longlong, c_int]
+    L.adtomo_nccl_finalize.restype = c_int
+    L.adtomo_nccl_finalize.argtypes = [_vp]
     _lib = L
     return L
 
@@ -156,6 +164,23 @@ class Context:
     @property
     def launch_count(self):
         return int(self._lib.adtomo_launch_count(self.handle))
+
+    # ---- NCCL (one all-reduce of the packed [grad | misfit] buffer per evaluation) -------------
+    @staticmethod
+    def nccl_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        check(load_library().adtomo_nccl_unique_id(buf), "adtomo_nccl_unique_id")
+        return buf.raw
+
+    def nccl_init(self, unique_id, rank, nranks):
+        check(self._lib.adtomo_nccl_init(self.handle, unique_id, int(rank), int(nranks)), "adtomo_nccl_init")
+
+    def nccl_allreduce_sum(self, buf, count=None, loc=HOST):
+        n = int(count if count is not None else (buf.size if isinstance(buf, np.ndarray) else buf.numel()))
+        check(self._lib.adtomo_nccl_allreduce_sum(self.handle, ptr(buf), n, loc), "adtomo_nccl_allreduce_sum")
+
+    def nccl_finalize(self):
+        check(self._lib.adtomo_nccl_finalize(self.handle), "adtomo_nccl_finalize")
 
     # ---- batched 3D --------------------------------------------------------------------------
     def forward3d_batch(self, u, u0, f, h, dims, tol, S, max_rounds=0, rounds=None, loc=HOST):

@@ -5,4 +5,4 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
-      -Xcompiler -fPIC -shared ${NVCC_EXTRA} -o ../libadtomo_b200.so capi.cu -lcudart
+      -Xcompiler -fPIC -shared ${NVCC_EXTRA} -o ../libadtomo_b200.so capi.cu -lcudart -ldl

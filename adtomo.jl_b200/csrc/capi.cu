@@ -15,6 +15,7 @@
 #include "kernels_v0.cuh"
 #include "kernels_adj_topo.cuh"
 #include "kernels_fwd_v1.cuh"
+#include "nccl_dyn.h"
 
 using namespace adtomo;
 
@@ -51,6 +52,8 @@ struct adtomo_ctx {
     std::vector<std::pair<int, int>> ev_used;   // (phase, pool index)
     std::vector<struct PlanCache *> plans;      // level-major layout plans, one per grid shape
     int fwd_variant = 0;                        // tuning aid: ADTOMO_FWD_VARIANT selects <threads, nodes per lane>
+    NcclApi::Comm nccl_comm = nullptr;          // set by adtomo_nccl_init
+    int nccl_rank = 0, nccl_size = 1;
     int force_cluster = 0;                      // testing aid: ADTOMO_FORCE_CLUSTER=2|4|8 splits every source over a cluster
     int force_v0 = 0;                           // debugging aid: ADTOMO_FORCE_V0=1 selects the row-major kernel
 };
@@ -111,6 +114,7 @@ static int ws_get(adtomo_ctx *c, const char *name, size_t bytes, void **out) {
         ptr = (type *)p__;                                                           \
     } while (0)
 
+extern "C" int adtomo_nccl_finalize(adtomo_ctx *c);
 extern "C" const char *adtomo_last_error(void) { return g_err.c_str(); }
 extern "C" int adtomo_version(void) { return 100; }
 
@@ -152,6 +156,7 @@ extern "C" int adtomo_destroy(adtomo_ctx *c) {
         if (pc->d_tables) cudaFree(pc->d_tables);
         delete pc;
     }
+    if (c->nccl_comm) adtomo_nccl_finalize(c);
     for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -875,4 +880,76 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
         for (int s = 0; s < S; s++)
             if (hs[s] < 0) return ADTOMO_ADJOINT_FLAGGED;
     return st;
+}
+
+// ---------------------------------------------------------------------------------------
+// NCCL: one all-reduce of the packed [grad_f | misfit] buffer per loss/gradient evaluation
+// (replaces mpi_bcast's backward + mpi_sum of scripts/inversion.jl:44,123)
+// ---------------------------------------------------------------------------------------
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static int nccl_ready() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    const char *why = "";
+    if (!g_nccl.load(&why)) return fail(ADTOMO_ERR_NCCL, "cannot load NCCL: %s", why ? why : "?");
+    return 0;
+}
+#define NCK(call)                                                                              \
+    do {                                                                                       \
+        int r__ = (call);                                                                      \
+        if (r__ != 0) return fail(ADTOMO_ERR_NCCL, "%s -> %s", #call, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+extern "C" int adtomo_nccl_unique_id(char *id128) {
+    if (!id128) return fail(ADTOMO_ERR_ARG, "null id buffer");
+    int rc = nccl_ready();
+    if (rc) return rc;
+    NcclApi::UniqueId id;
+    NCK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+extern "C" int adtomo_nccl_init(adtomo_ctx *c, const char *id128, int rank, int nranks) {
+    if (!c || !id128) return fail(ADTOMO_ERR_ARG, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ADTOMO_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    int rc = nccl_ready();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    if (c->nccl_comm) return fail(ADTOMO_ERR_ARG, "context already has a communicator");
+    NcclApi::UniqueId id;
+    memcpy(id.internal, id128, 128);
+    NCK(g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank));
+    c->nccl_rank = rank;
+    c->nccl_size = nranks;
+    return 0;
+}
+
+extern "C" int adtomo_nccl_allreduce_sum(adtomo_ctx *c, double *buf, long long count, int loc) {
+    if (!c || !buf || count < 0) return fail(ADTOMO_ERR_ARG, "bad argument");
+    if (!c->nccl_comm) return fail(ADTOMO_ERR_NCCL, "adtomo_nccl_init has not been called on this context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    double *d = buf;
+    if (loc == ADTOMO_HOST) {
+        WS(c, "nccl_stage", double, (size_t)count, d);
+        CK(cudaMemcpyAsync(d, buf, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
+    }
+    NCK(g_nccl.AllReduce(d, d, (size_t)count, NcclApi::kFloat64, NcclApi::kSum, c->nccl_comm, c->stream));
+    if (loc == ADTOMO_HOST) CK(cudaMemcpyAsync(buf, d, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int adtomo_nccl_finalize(adtomo_ctx *c) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "null context");
+    if (c->nccl_comm) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        g_nccl.CommDestroy(c->nccl_comm);
+        c->nccl_comm = nullptr;
+    }
+    return 0;
 }

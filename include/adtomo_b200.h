@@ -113,6 +113,19 @@ int adtomo_eikonal3d_misfit_grad(adtomo_ctx *ctx, double *misfit, double *grad_f
                                  const double *rcv_xyz, const double *uobs, const double *qua, int *rounds,
                                  int loc);
 
+/* ---- multi-GPU: source shards + ONE all-reduce per evaluation ---------------------------- */
+/* Replaces the MPI plumbing of the drivers (mpi_bcast / mpi_sum, scripts/inversion.jl:44,123;
+ * flag protocol of src/mpi_optimize.jl:11-33): one process per GPU, rank r evaluates sources
+ * r, r+P, ... with adtomo_eikonal3d_misfit_grad and sums the packed N+1 buffer over ranks.
+ * NCCL is loaded with dlopen("libnccl.so.2") on first use (the library itself does not link it).
+ * Rank 0 creates the 128-byte id and distributes it by any means (file, socket, MPI, torchrun). */
+int adtomo_nccl_unique_id(char *id128);
+int adtomo_nccl_init(adtomo_ctx *ctx, const char *id128, int rank, int nranks);
+/* In-place sum over ranks of `count` doubles (ncclAllReduce on the context's stream; loc = HOST
+ * stages through the workspace).  Returns after the result is complete. */
+int adtomo_nccl_allreduce_sum(adtomo_ctx *ctx, double *buf, long long count, int loc);
+int adtomo_nccl_finalize(adtomo_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif
