@@ -15,6 +15,7 @@
 #include "kernels_v0.cuh"
 #include "kernels_adj_topo.cuh"
 #include "kernels_fwd_v1.cuh"
+#include "kernels_fwd_v2.cuh"
 #include "nccl_dyn.h"
 
 using namespace adtomo;
@@ -56,6 +57,21 @@ struct adtomo_ctx {
     int nccl_rank = 0, nccl_size = 1;
     int force_cluster = 0;                      // testing aid: ADTOMO_FORCE_CLUSTER=2|4|8 splits every source over a cluster
     int force_v0 = 0;                           // debugging aid: ADTOMO_FORCE_V0=1 selects the row-major kernel
+    int force_v1 = 0;                           // debugging aid: ADTOMO_FORCE_V1=1 selects the level-major kernel
+    int v2_occ = 0;                             // tuning aid: ADTOMO_V2_OCC caps the CTAs per SM of the skewed-pencil kernel
+    std::vector<struct Plan2Cache *> plans2;    // skewed-pencil plans, one per grid shape
+    // the +inf padding of the skewed-pencil field buffers is written once per (buffer, plan, sources)
+    void *v2_pad_ptr = nullptr;
+    size_t v2_pad_bytes = 0;
+    const struct Plan2Cache *v2_pad_plan = nullptr;
+    int v2_pad_S = 0;
+};
+
+struct Plan2Cache {
+    int m, n, l;
+    bool ok;
+    Plan2 plan;
+    size_t smem_bytes;
 };
 
 struct PlanCache {
@@ -138,6 +154,10 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     CK(cudaEventCreate(&c->ev1));
     const char *fv0 = getenv("ADTOMO_FORCE_V0");
     c->force_v0 = (fv0 && fv0[0] == '1');
+    const char *fv1 = getenv("ADTOMO_FORCE_V1");
+    c->force_v1 = (fv1 && fv1[0] == '1');
+    const char *vocc = getenv("ADTOMO_V2_OCC");
+    c->v2_occ = vocc ? atoi(vocc) : 0;
     const char *fvv = getenv("ADTOMO_FWD_VARIANT");
     c->fwd_variant = fvv ? atoi(fvv) : 0;
     const char *fcl = getenv("ADTOMO_FORCE_CLUSTER");
@@ -157,6 +177,7 @@ extern "C" int adtomo_destroy(adtomo_ctx *c) {
         delete pc;
     }
     if (c->nccl_comm) adtomo_nccl_finalize(c);
+    for (auto *pc : c->plans2) delete pc;
     for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -346,9 +367,75 @@ static int launch_fwd(adtomo_ctx *c, K kern, int NT, const FwdCfg &cfg, const Pl
     return 0;
 }
 
+static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
+    for (auto *pc : c->plans2)
+        if (pc->m == m && pc->n == n && pc->l == l) return pc;
+    Plan2Cache *pc = new Plan2Cache();
+    pc->m = m; pc->n = n; pc->l = l;
+    // 16 warps: two CTAs per SM (64 registers per thread); 32 warps when a row needs more column groups
+    const char *vw = getenv("ADTOMO_V2_WARPS");      // tuning aid
+    pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
+    if (!pc->ok) pc->ok = v2_build_plan(pc->plan, m, n, l, 32, 96 * 1024);
+    pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
+    c->plans2.push_back(pc);
+    return pc;
+}
+
+// Skewed-pencil path (kernels_fwd_v2.cuh): convert in, sweep, convert out.
+static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const double *df, const Dims3 &d, double h,
+                    double tol, int max_rounds, int S, int *d_rounds, double *d_errs) {
+    const Plan2 &P = pc->plan;
+    double *bufs, *flay;
+    int *where;
+    const size_t nb = (size_t)S * 3 * P.M;
+    WS(c, "fwd2_bufs", double, nb, bufs);
+    WS(c, "fwd2_flay", double, (size_t)2 * P.M, flay);
+    WS(c, "fwd2_where", int, S, where);
+    int pk = phase_begin(c, PH_CONVERT);
+    if (c->v2_pad_ptr != (void *)bufs || c->v2_pad_plan != pc || c->v2_pad_S < S || c->v2_pad_bytes != c->ws["fwd2_bufs"].second) {
+        // every slot that is not a grid node must hold +inf; nothing ever writes those slots afterwards
+        k2_fill<<<c->num_sms * 8, 512, 0, c->stream>>>(bufs, (long long)nb, v2_inf());
+        LAUNCHED(c, "k2_fill");
+        c->v2_pad_ptr = bufs; c->v2_pad_plan = pc; c->v2_pad_S = S; c->v2_pad_bytes = c->ws["fwd2_bufs"].second;
+    }
+    const int eb = elem_grid(c, d.N);
+    k2_f_to_layouts<<<eb, 256, 0, c->stream>>>(P, df, flay, flay + P.M);
+    LAUNCHED(c, "k2_f_to_layouts");
+    k2_u0_to_P<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, dU, bufs);
+    LAUNCHED(c, "k2_u0_to_P");
+    phase_end(c, pk);
+    pk = phase_begin(c, PH_FWD);
+    if (P.NT <= 512) {
+        auto kern = k_fwd3d_v2<512, 2>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));
+        if (occ < 1) occ = 1;
+        if (c->v2_occ > 0 && occ > c->v2_occ) occ = c->v2_occ;
+        kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol, max_rounds,
+                                                                                 S, d_rounds, d_errs, where);
+    } else {
+        auto kern = k_fwd3d_v2<1024, 1>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        kern<<<std::min(S, c->num_sms), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol, max_rounds, S,
+                                                                           d_rounds, d_errs, where);
+    }
+    phase_end(c, pk);
+    LAUNCHED(c, "k_fwd3d_v2");
+    pk = phase_begin(c, PH_CONVERT);
+    k2_P_to_rowmajor<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, bufs, where, dU);
+    phase_end(c, pk);
+    LAUNCHED(c, "k2_P_to_rowmajor");
+    return 0;
+}
+
 // dU: S x N row-major, holds u0 on entry and the travel times on exit.
 static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3 &d, double h, double tol,
                         int max_rounds, int S, int *d_rounds, double *d_errs) {
+    if (!c->force_v0 && !c->force_v1 && !c->force_cluster) {
+        const Plan2Cache *p2 = get_plan2(c, d.m, d.n, d.l);
+        if (p2->ok) return fwd3d_v2(c, p2, dU, df, d, h, tol, max_rounds, S, d_rounds, d_errs);
+    }
     PlanCache *pc = nullptr;
     int rc = get_plan(c, d.m, d.n, d.l, &pc);
     if (rc) return rc;

@@ -1,0 +1,468 @@
+// kernels_fwd_v2.cuh -- 3D forward fast sweeping on SKEWED-PENCIL layouts.
+//
+// Reference semantics: Eikonal3D.cpp:35-57 (one directional Gauss-Seidel sweep), :59-68 (the 8
+// sweeps of a round), :71-88 (rounds until max|u - u_old| < tol, cap 20).  A sweep is executed level
+// by level (level = A'+W'+C' with every coordinate counted in the sweep's direction): the nodes of a
+// level are independent, take NEW values from level-1 and OLD values from level+1, which reproduces
+// the serial lexicographic sweep bit for bit.
+//
+// The level-major kernel (kernels_fwd_v1.cuh) spends ~185 of its ~290 instructions per 32 node
+// updates on index arithmetic (packed level enumeration, boundary predicates, next-layout offsets).
+// Here the three grid axes get fixed ROLES (A = row axis, W = walk axis, C = lane axis) and a field
+// is stored skewed:   slot(A, mu, C),  mu = W + C  (layout P)   or   mu = W + (dC-1-C)  (layout M),
+// offset ((A+1)*RS + mu+1)*PC + C.  A thread owns PENCILS (A, C) and walks them along mu, one node
+// per level:
+//   * all six neighbours sit at CONSTANT offsets from the node (global: A+-1 -> +-RS*PC,
+//     W+-1 -> +-PC, C+-1 -> +-(PC+-1)), the offset of a
+//     pencil advances by a constant per level, and the sweep direction only changes the SIGNS of
+//     those constants: one code path, no per-node index decode;
+//   * every slot that is not a grid node (skew padding, one pad row/column/slab around the box) holds
+//     +inf forever, so the reference's mirror rule (Eikonal3D.cpp:47-52: a missing neighbour is
+//     replaced by the existing one) is min(x, +inf) and needs NO boundary predicate;
+//   * sweeps whose (W,C) signs agree run on layout P, the others on M; consecutive sweeps on the same
+//     layout update the field IN PLACE.  The reference order needs 4 layout changes per round
+//     (P P M M P M M P); each is a re-skew of every A-slab through a shared-memory plane, coalesced
+//     and with full lanes on both sides.  (Measured alternative: letting the sweep before a change
+//     scatter its results into the other layout -- the 4 doubles of a sector arrive 2 levels apart,
+//     and with 256 sources in flight the partially written sectors overflow L2: 3.5x the DRAM bytes.)
+//   * lanes of a warp cover a patch of 4 rows x 8 columns of pencils (a warp slot), so a slot is live
+//     for dW + 10 levels of which dW are fully used (128 -> 93 %); the live slots of a level are dealt
+//     round-robin to the warps.
+// Upwind (new) values are read back from global memory: they were stored by threads of the same CTA
+// one level (one __syncthreads) earlier, so they are visible, and they sit at the mirrored constant
+// offsets.  The sweep therefore needs NO shared memory (the level-major kernel needs two sheets of
+// (dA+2) x pitch doubles, 137 KB for 128x128x64, which pins it to one CTA per SM and to grids whose
+// sheets fit): two CTAs (= two sources) share an SM and fill each other's barrier and load stalls,
+// and any grid size runs on a single CTA per source.
+// Buffers per source: three fields o/a (layout P) and z (layout M).  Sweep 1 of a round reads o and
+// writes a (o stays as the round-start field for the L-inf stopping test, fused into sweep 8).
+#pragma once
+#include "eik_core.h"
+
+namespace adtomo {
+
+constexpr int V2_LA = 4;   // rows of the lane patch
+constexpr int V2_LC = 8;   // columns of the lane patch
+
+struct Plan2 {
+    int ext[3];          // m, n, l
+    int role[3];         // grid axis (0=i,1=j,2=k) playing A, W, C
+    int dA, dW, dC;
+    int nmu;             // dW + dC - 1 skewed rows per slab
+    int RS;              // rows per slab incl. one pad row each side = nmu + 2
+    int PC;              // row pitch (>= dC+1, multiple of 4)
+    int nlev;            // dA + dW + dC - 2
+    int G, R;            // column groups per row block, row blocks per step; warps = G*R
+    int NT;              // threads = 32*G*R
+    int WCH, PS;         // re-skew: W rows per pass, plane pitch (even)
+    long long M;         // slots per field buffer = (dA+2)*RS*PC
+    long long N;
+    int sg[8][3];        // (sA, sW, sC) of the reference's 8 sweeps (Eikonal3D.cpp:59-68) by role
+};
+
+#define V2_INF_BITS 0x7ff0000000000000LL
+
+EIK_HD double v2_inf() {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(V2_INF_BITS);
+#else
+    return INFINITY;
+#endif
+}
+
+// slot of node (A, W, C) in layout sigma (+1: P, -1: M)
+EIK_HD long long v2_offset(const Plan2 &P, int A, int W, int C, int sigma) {
+    const int mu = W + (sigma > 0 ? C : P.dC - 1 - C);
+    return ((long long)(A + 1) * P.RS + (mu + 1)) * P.PC + C;
+}
+
+// slot of grid node (i,j,k)
+EIK_HD long long v2_offset_ijk(const Plan2 &P, int i, int j, int k, int sigma) {
+    const int x[3] = {i, j, k};
+    return v2_offset(P, x[P.role[0]], x[P.role[1]], x[P.role[2]], sigma);
+}
+
+// Live row blocks of column group g at level lam: rb in [lo, lo+n).  A row block is LA rows of
+// pencils, a column group LC columns; the block is live when some pencil (A', C') in it has
+// 0 <= lam - A' - C' < dW (coordinates counted in the sweep's direction).
+template <int SC>
+EIK_HD void v2_window(const Plan2 &P, const int g, const int lam, int &lo, int &n) {
+    const int c_lo = g * V2_LC, c_hi = (g * V2_LC + V2_LC - 1 < P.dC - 1) ? g * V2_LC + V2_LC - 1 : P.dC - 1;
+    const int cpmin = SC > 0 ? c_lo : P.dC - 1 - c_hi;       // C' range of the group (columns beyond dC excluded)
+    const int cpmax = SC > 0 ? c_hi : P.dC - 1 - c_lo;
+    const int nrb = (P.dA + V2_LA - 1) / V2_LA;
+    const int t = lam - cpmin;
+    int hi = t >= 0 ? t / V2_LA : -1;
+    if (hi > nrb - 1) hi = nrb - 1;
+    const int lo_n = lam - (P.dW - 1 + cpmax + V2_LA - 1);
+    lo = lo_n > 0 ? (lo_n + V2_LA - 1) / V2_LA : 0;
+    n = hi - lo + 1;
+    if (n < 0 || g >= P.G) n = 0;
+}
+
+// Per-lane constants of one sweep: lane = (la, lc) inside the LA x LC patch of pencils.
+struct V2Lane {
+    int offc;   // slot = offc + rb*offRB + lam*offW + g*LC
+    int wqc;    // W'   = wqc + lam - rb*LA - SC*g*LC
+    int la, lc;
+};
+
+template <int SA, int SW, int SC>
+EIK_HD V2Lane v2_lane_setup(const Plan2 &P, const int lane) {
+    V2Lane L;
+    L.la = lane / V2_LC;
+    L.lc = lane % V2_LC;
+    L.offc = ((SA > 0 ? L.la + 1 : P.dA - L.la) * P.RS + (SW > 0 ? 1 - L.la : P.nmu + L.la)) * P.PC + L.lc;
+    L.wqc = -L.la - (SC > 0 ? L.lc : P.dC - 1 - L.lc);
+    return L;
+}
+
+// One lane's node of warp slot (rb, g) at level lam of a sweep with signs (SA, SW, SC) by role.
+// OOP: rd != wr (sweep 1 of a round), else the field is updated in place; CMP: fold |new - cmp| into
+// err (sweep 8).
+template <int SA, int SW, int SC, bool OOP, bool CMP>
+EIK_HD void v2_node(const Plan2 &P, const V2Lane &L, const int lam, const int rb, const int g, const double *rd,
+                    double *wr, const double *__restrict__ fl, const double *cmp, const double h, double &err) {
+    const int offA = SA * P.RS * P.PC, offW = SW * P.PC, offC = SW * P.PC + SC;   // downwind (old, level+1)
+    const int offRB = V2_LA * (SA * P.RS - SW) * P.PC;
+    const int wq = L.wqc + lam - rb * V2_LA - SC * g * V2_LC;
+    if ((unsigned)wq >= (unsigned)P.dW || rb * V2_LA + L.la >= P.dA || g * V2_LC + L.lc >= P.dC) return;
+    const int off = L.offc + rb * offRB + lam * offW + g * V2_LC;
+    const double *p = rd + off;
+    const double own = p[0];
+    const double fv = fl[off];
+    const double dA_ = p[offA];
+    const double dW_ = p[offW];
+    const double dC_ = p[offC];
+#if defined(__CUDA_ARCH__)
+    if ((unsigned)(wq + 2) < (unsigned)P.dW) {   // the node this pencil reaches two levels ahead, its f one level ahead
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2 * offW));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(fl + off + offW));
+    }
+#endif
+    // upwind neighbours (new values of level-1, stored one barrier ago by this CTA); OOP: they live in wr
+    const double *pu = OOP ? (const double *)wr + off : p;
+    const double uA = pu[-offA];
+    const double uW = pu[-offW];
+    const double uC = pu[-offC];
+    double a1 = eik_min(uA, dA_), a2 = eik_min(uW, dW_), a3 = eik_min(uC, dC_);
+    double res = own;
+    eik_sort3(a1, a2, a3);
+    bool changed = false;
+    if (a1 < own) {   // otherwise the candidate (> a1) cannot win the min: exact skip
+        const double un = eik_solve3_sorted(a1, a2, a3, fv * h, fv * fv * h * h);
+        if (un < own) { res = un; changed = true; }
+    }
+    if (OOP || changed) wr[off] = res;
+    if (CMP) {
+        const double dd = fabs(res - cmp[off]);
+        err = (err < dd) ? dd : err;
+    }
+}
+
+// dispatch on the signs of sweep sw (sweeps 0 and 7 are (+,+,+) and (-,-,-) under every role assignment)
+#define V2_DISPATCH(P, sw, CALL)                                                           \
+    do {                                                                                   \
+        if ((sw) == 0) { CALL(1, 1, 1, true, false); }                                     \
+        else if ((sw) == 7) { CALL(-1, -1, -1, false, true); }                             \
+        else {                                                                             \
+            const int code__ = ((P).sg[sw][0] > 0 ? 4 : 0) | ((P).sg[sw][1] > 0 ? 2 : 0) | ((P).sg[sw][2] > 0 ? 1 : 0); \
+            switch (code__) {                                                              \
+                case 1: CALL(-1, -1, 1, false, false); break;                              \
+                case 2: CALL(-1, 1, -1, false, false); break;                              \
+                case 3: CALL(-1, 1, 1, false, false); break;                               \
+                case 4: CALL(1, -1, -1, false, false); break;                              \
+                case 5: CALL(1, -1, 1, false, false); break;                               \
+                default: CALL(1, 1, -1, false, false); break;                              \
+            }                                                                              \
+        }                                                                                  \
+    } while (0)
+
+// Re-skew of W-chunk [w0, w0+wc) of slab A between the layouts, through `plane` (wc x PS doubles).
+// The chunk is enumerated by VIRTUAL rows v in [0, wc) x columns C: element (v, C) is the node
+// W = w0 + ((v - cc) mod wc), cc = C (layout P) or dC-1-C (layout M), which lies in row mu = W + cc of
+// that layout.  A virtual row is made of pieces of the physical rows w0+v, w0+v+wc, ...: every lane
+// has a node, and each piece is a contiguous run of C, i.e. coalesced.
+// phase 0: rows of layout sigmaFrom -> plane;  phase 1: plane -> rows of the other layout.
+// Index map of element (v, C): plane slot and offset inside the slab (layout sigma).
+EIK_HD void v2_reskew_index(const Plan2 &P, const int sigma, const int w0, const int wc, const int v, const int C,
+                            int &pl, int &go) {
+    const int cc = sigma > 0 ? C : P.dC - 1 - C;
+    int Wl = v - cc;                       // local W in [0, wc)
+    while (Wl < 0) Wl += wc;
+    pl = Wl * P.PS + C;
+    go = (w0 + Wl + cc + 1) * P.PC + C;
+}
+
+EIK_HD void v2_reskew_elem(const Plan2 &P, const double *src, double *dst, const int sigmaFrom, double *plane,
+                           const long long slab, const int w0, const int wc, const int phase, const int v, const int C) {
+    int pl, go;
+    v2_reskew_index(P, phase == 0 ? sigmaFrom : -sigmaFrom, w0, wc, v, C, pl, go);
+    if (phase == 0) plane[pl] = src[slab + go];
+    else dst[slab + go] = plane[pl];
+}
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ double v2_block_max(double v, double *red) {
+    for (int o = 16; o > 0; o >>= 1) {
+        double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (w > v) ? w : v;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = red[0];
+    const int nw = blockDim.x >> 5;
+    for (int w = 1; w < nw; w++) r = (red[w] > r) ? red[w] : r;
+    return r;
+}
+
+// One sweep.  Per level the live warp slots (row block x column group) are enumerated group by group
+// and dealt round-robin to the warps: lane g of every warp computes group g's window, a warp scan gives
+// the slot ranges, and slot q is located with one ballot (fixed pencil ownership left the slowest warp
+// with 1.5x the mean work per level).
+template <int SA, int SW, int SC, bool OOP, bool CMP>
+__device__ __forceinline__ void v2_sweep(const Plan2 &P, const double *rd, double *wr,
+                                         const double *__restrict__ fl, const double *cmp, const double h,
+                                         double &err) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const V2Lane L = v2_lane_setup<SA, SW, SC>(P, lane);
+    __syncthreads();     // the previous sweep wrote the field this sweep reads
+    for (int lam = 0; lam < P.nlev; lam++) {
+        int lo, n;
+        v2_window<SC>(P, lane, lam, lo, n);
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - n;
+        // slot q -> (g, rb); while a slot is computed, the lines holding the NEXT slot's upwind neighbours
+        // (stored one level ago, i.e. in L2 but not in this SM's L1) are pulled into L1
+#define V2_MAP(q_, g_, rb_)                                                                           \
+    do {                                                                                              \
+        const unsigned m__ = __ballot_sync(0xffffffffu, excl <= (q_) && n > 0);                       \
+        g_ = 31 - __clz((int)m__);                                                                    \
+        rb_ = __shfl_sync(0xffffffffu, lo, g_) + (q_) - __shfl_sync(0xffffffffu, excl, g_);           \
+    } while (0)
+        int q = warp, g = 0, rb = 0;
+        if (q < total) V2_MAP(q, g, rb);
+        while (q < total) {
+            const int qn = q + nw;
+            int gn = 0, rbn = 0;
+            if (qn < total) {
+                V2_MAP(qn, gn, rbn);
+                const double *pn = (OOP ? (const double *)wr : rd) + (L.offc + rbn * (V2_LA * (SA * P.RS - SW) * P.PC) + lam * (SW * P.PC) + gn * V2_LC);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pn - SA * P.RS * P.PC));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pn - SW * P.PC));
+            }
+            v2_node<SA, SW, SC, OOP, CMP>(P, L, lam, rb, g, rd, wr, fl, cmp, h, err);
+            q = qn; g = gn; rb = rbn;
+        }
+#undef V2_MAP
+        __syncthreads();
+    }
+}
+
+// Re-skew of a whole field: slab by slab, chunk by chunk; two barriers per chunk.  A warp takes
+// virtual rows v = warp, warp+nw, ..., four at a time (four loads in flight before the first store).
+__device__ __forceinline__ void v2_reskew(const Plan2 &P, const double *src, double *dst, const int sigmaFrom,
+                                          double *plane) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int A = 0; A < P.dA; A++) {
+        const double *s = src + (long long)(A + 1) * P.RS * P.PC;
+        double *d = dst + (long long)(A + 1) * P.RS * P.PC;
+        for (int w0 = 0; w0 < P.dW; w0 += P.WCH) {
+            const int wc = (P.dW - w0 < P.WCH) ? P.dW - w0 : P.WCH;
+            for (int C = lane; C < P.dC; C += 32) {
+                for (int v = warp; v < wc; v += 4 * nw) {
+                    int pl[4], go[4];
+                    double x[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int vj = (v + j * nw < wc) ? v + j * nw : v;     // clamp: duplicates rewrite the same value
+                        v2_reskew_index(P, sigmaFrom, w0, wc, vj, C, pl[j], go[j]);
+                        x[j] = s[go[j]];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) plane[pl[j]] = x[j];
+                }
+            }
+            __syncthreads();
+            for (int C = lane; C < P.dC; C += 32) {
+                for (int v = warp; v < wc; v += 4 * nw) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (v + j * nw < wc) {
+                            int pl, go;
+                            v2_reskew_index(P, -sigmaFrom, w0, wc, v + j * nw, C, pl, go);
+                            d[go] = plane[pl];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// bufs: S x 3 x M doubles; buffer 0 of every source holds u0 in layout P on entry, every slot that
+// is not a grid node holds +inf in all three buffers.  fP/fM: the slowness in layouts P and M.
+// where[src] receives the index (0..2) of the buffer holding the result (layout P).
+// One CTA per source at a time; sources are assigned statically (block-uniform control flow).
+// Dynamic shared memory: the re-skew plane, WCH x PS doubles.
+template <int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v2(const Plan2 P, double *bufs,
+                                                          const double *__restrict__ fP, const double *__restrict__ fM,
+                                                          const double h, const double tol, const int max_rounds,
+                                                          const int S, int *__restrict__ rounds, double *__restrict__ errs,
+                                                          int *__restrict__ where) {
+    extern __shared__ double plane[];
+    __shared__ double red[32];
+    for (int src = blockIdx.x; src < S; src += gridDim.x) {
+        double *B3 = bufs + (long long)src * 3 * P.M;
+        int o = 0, a = 1;          // layout P: round-start field, working field;  buffer 2: layout M
+        double *Bz = B3 + 2 * P.M;
+        int r = 0;
+        bool conv = false;
+        while (r < max_rounds) {
+            double err = 0.0;
+            double *Bo = B3 + o * P.M, *Ba = B3 + a * P.M;
+            int state = 1;                        // layout of the working field
+            double *w = Ba;
+            for (int sw = 0; sw < 8; sw++) {
+                const int sigma = P.sg[sw][1] * P.sg[sw][2];
+                if (sw > 0 && sigma != state) {
+                    double *dst = state > 0 ? Bz : Ba;
+                    __syncthreads();
+                    v2_reskew(P, w, dst, state, plane);
+                    w = dst;
+                    state = sigma;
+                }
+#define V2_CALL(a_, w_, c_, oop_, cmp_) v2_sweep<a_, w_, c_, oop_, cmp_>(P, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err)
+                V2_DISPATCH(P, sw, V2_CALL);
+#undef V2_CALL
+            }
+            const double e = v2_block_max(err, red);
+            if (threadIdx.x == 0 && errs) errs[(long long)src * max_rounds + r] = e;
+            r++;
+            const int oo = o; o = a; a = oo;      // the result (in a) becomes next round's round-start field
+            if (__any_sync(0xffffffffu, e < tol)) { conv = true; break; }   // e is block-uniform; the vote makes that visible
+        }
+        if (threadIdx.x == 0) {
+            if (rounds) rounds[src] = conv ? r : -r;
+            where[src] = o;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion (elementwise, once per call)
+// ---------------------------------------------------------------------------------------------
+__global__ void k2_fill(double *__restrict__ p, const long long n, const double v) {
+    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x) p[id] = v;
+}
+
+// f (row-major) -> layouts P and M
+__global__ void k2_f_to_layouts(const Plan2 P, const double *__restrict__ f, double *__restrict__ fP, double *__restrict__ fM) {
+    const int n = P.ext[1], l = P.ext[2];
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < P.N; id += gridDim.x * blockDim.x) {
+        const int k = id % l, t = id / l, j = t % n, i = t / n;
+        const double v = f[id];
+        fP[v2_offset_ijk(P, i, j, k, +1)] = v;
+        fM[v2_offset_ijk(P, i, j, k, -1)] = v;
+    }
+}
+
+// dense row-major u0 (S x N) -> buffer 0 of each source, layout P.  grid: (blocks, S)
+__global__ void k2_u0_to_P(const Plan2 P, const double *__restrict__ U0, double *__restrict__ bufs) {
+    const int n = P.ext[1], l = P.ext[2];
+    const int src = blockIdx.y;
+    const double *u0 = U0 + (long long)src * P.N;
+    double *b0 = bufs + (long long)src * 3 * P.M;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < P.N; id += gridDim.x * blockDim.x) {
+        const int k = id % l, t = id / l, j = t % n, i = t / n;
+        b0[v2_offset_ijk(P, i, j, k, +1)] = u0[id];
+    }
+}
+
+// result (layout P, buffer where[src]) -> dense row-major U (S x N).  grid: (blocks, S)
+__global__ void k2_P_to_rowmajor(const Plan2 P, const double *__restrict__ bufs, const int *__restrict__ where,
+                                 double *__restrict__ U) {
+    const int n = P.ext[1], l = P.ext[2];
+    const int src = blockIdx.y;
+    const double *b = bufs + ((long long)src * 3 + where[src]) * P.M;
+    double *u = U + (long long)src * P.N;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < P.N; id += gridDim.x * blockDim.x) {
+        const int k = id % l, t = id / l, j = t % n, i = t / n;
+        u[id] = b[v2_offset_ijk(P, i, j, k, +1)];
+    }
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// host: plan construction
+// ---------------------------------------------------------------------------------------------
+// Chooses the axis roles (A, W, C) for an m x n x l grid: lanes fill best when dC is a multiple of 8,
+// a warp is live for dW + 10 levels of which dW are fully used, and role assignments with A = k need 6
+// instead of 4 layout changes per round.  max_warps: warps per CTA (16: two CTAs per SM at 64 registers).
+// Returns false when the grid cannot be handled (column groups exceed the warps, 32-bit slots).
+inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int max_warps, size_t plane_bytes) {
+    static const int SG[8][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, -1, 1}, {1, -1, 1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, -1}};
+    const int ext[3] = {m, n, l};
+    double best = -1.0;
+    int bestRole[3] = {0, 1, 2};
+    static const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    for (int p = 0; p < 6; p++) {
+        const int dA = ext[perms[p][0]], dW = ext[perms[p][1]], dC = ext[perms[p][2]];
+        const int G = (dC + V2_LC - 1) / V2_LC;
+        if (G > max_warps) continue;
+        // layout changes per round (sigma = sW*sC along the reference's sweep order, cyclic)
+        int changes = 0;
+        for (int s = 0; s < 8; s++) {
+            const int s0 = SG[s][perms[p][1]] * SG[s][perms[p][2]];
+            const int s1 = SG[(s + 1) % 8][perms[p][1]] * SG[(s + 1) % 8][perms[p][2]];
+            changes += (s0 != s1);
+        }
+        const double fill = (double)dC / (V2_LC * G);
+        const double live = (double)dW / (dW + V2_LC + V2_LA - 2);
+        const int nrb = (dA + V2_LA - 1) / V2_LA;
+        int R = max_warps / G;
+        if (R > nrb) R = nrb;
+        const double rowfill = (double)nrb / (((nrb + R - 1) / R) * R);   // idle warps when few row blocks
+        const double afill = (double)dA / (nrb * V2_LA);
+        const double warps = (double)(G * R) / max_warps;                 // unused warp slots
+        double score = fill * live * rowfill * afill * (0.5 + 0.5 * warps) * (1.0 - 0.012 * changes);
+        if (perms[p][2] == 2) score *= 1.01;      // tie-break: lanes along the grid's fastest axis
+        if (score > best) { best = score; for (int q = 0; q < 3; q++) bestRole[q] = perms[p][q]; }
+    }
+    if (best < 0) return false;
+    for (int q = 0; q < 3; q++) { P.ext[q] = ext[q]; P.role[q] = bestRole[q]; }
+    P.dA = ext[P.role[0]]; P.dW = ext[P.role[1]]; P.dC = ext[P.role[2]];
+    P.nmu = P.dW + P.dC - 1;
+    P.RS = P.nmu + 2;
+    P.PC = ((P.dC + 1 + 3) / 4) * 4;
+    P.nlev = P.dA + P.dW + P.dC - 2;
+    P.G = (P.dC + V2_LC - 1) / V2_LC;
+    P.R = max_warps / P.G;
+    const int nrb = (P.dA + V2_LA - 1) / V2_LA;
+    if (P.R > nrb) P.R = nrb;
+    P.NT = 32 * P.G * P.R;
+    P.PS = (P.dC + 1) & ~1;
+    P.WCH = (int)(plane_bytes / (sizeof(double) * P.PS));
+    if (P.WCH > P.dW) P.WCH = P.dW;
+    if (P.WCH < 1) return false;
+    P.N = (long long)m * n * l;
+    P.M = (long long)(P.dA + 2) * P.RS * P.PC;
+    if (P.M >= (1LL << 31) - 4 * (long long)P.RS * P.PC) return false;   // 32-bit slot arithmetic
+    for (int s = 0; s < 8; s++)
+        for (int q = 0; q < 3; q++) P.sg[s][q] = SG[s][P.role[q]];
+    return true;
+}
+
+}  // namespace adtomo

@@ -56,3 +56,60 @@ def test_emulated_kernel_bitexact(emul, oracle, dims, tol):
     assert abs(r) == r_ref and (r > 0) == (tol > 0)
     assert err.value == e_ref
     np.testing.assert_array_equal(u, u_ref)
+
+
+# ----------------------------------------------------------------------------------------------
+# skewed-pencil kernel (kernels_fwd_v2.cuh): the kernel's own per-thread functions run on the host
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emul2():
+    so = os.path.join(HERE, "emul", "libemul_v2.so")
+    src = os.path.join(HERE, "emul", "emulate_v2.cpp")
+    deps = [src] + [os.path.join(HERE, "..", "adtomo.jl_b200", "csrc", n) for n in ("kernels_fwd_v2.cuh", "eik_core.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
+    L = ctypes.CDLL(so)
+    L.emul_v2_forward.restype = ctypes.c_int
+    L.emul_v2_forward.argtypes = [_dp, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_longlong, _dp]
+    L.emul_v2_plan.restype = ctypes.c_int
+    L.emul_v2_plan.argtypes = [ctypes.c_int] * 4 + [ctypes.c_longlong, ctypes.POINTER(ctypes.c_int)]
+    return L
+
+
+PLANE = 64 * 1024
+
+
+@pytest.mark.parametrize("dims,tol,warps,plane", [
+    ((2, 2, 2), 1e-9, 16, PLANE), ((5, 4, 3), 1e-9, 16, PLANE), ((3, 9, 4), 1e-6, 16, PLANE), ((9, 7, 6), 1e-6, 16, PLANE),
+    ((12, 12, 12), 1e-3, 16, PLANE), ((7, 3, 11), 0.0, 16, PLANE), ((16, 12, 6), 1e-6, 16, PLANE),
+    ((6, 16, 12), 1e-6, 16, PLANE), ((12, 6, 16), 1e-4, 16, PLANE), ((24, 19, 15), 1e-3, 16, PLANE),
+    ((33, 9, 10), 1e-6, 16, PLANE), ((10, 35, 9), 1e-6, 16, PLANE), ((9, 10, 41), 1e-6, 16, PLANE),
+    ((21, 21, 21), 1e-9, 16, PLANE),
+    # few warps force other role assignments, a tiny plane forces a chunked re-skew (chunks shorter than dC too)
+    ((16, 12, 6), 1e-6, 1, 400), ((12, 6, 16), 1e-6, 1, 400), ((13, 17, 5), 1e-6, 2, 300), ((20, 18, 9), 1e-6, 2, 1000),
+    ((9, 40, 20), 1e-6, 4, 2000), ((40, 9, 20), 1e-6, 3, 700), ((20, 40, 9), 1e-6, 5, 700)])
+def test_emulated_v2_bitexact(emul2, oracle, dims, tol, warps, plane):
+    rng = np.random.default_rng(sum(dims) + 7)
+    f = 0.5 + rng.random(dims)
+    u0 = np.full(dims, 1000.0)
+    for _ in range(2):
+        u0[tuple(rng.integers(0, d) for d in dims)] = float(rng.random() * 0.1)
+    h = 0.3
+    u_ref, r_ref, e_ref = oracle.eikonal3d_forward(u0, f, h, tol)
+    u = u0.copy()
+    errs = np.zeros(20)
+    r = emul2.emul_v2_forward(u.ctypes.data_as(_dp), f.ctypes.data_as(_dp), *dims, h, tol, 20, warps, plane,
+                              errs.ctypes.data_as(_dp))
+    assert r > -1000, "no plan fits / pads were overwritten"
+    assert abs(r) == r_ref and (r > 0) == (tol > 0)
+    assert errs[abs(r) - 1] == e_ref
+    np.testing.assert_array_equal(u, u_ref)
+
+
+def test_v2_plan_roles(emul2):
+    out = (ctypes.c_int * 7)()
+    assert emul2.emul_v2_plan(128, 128, 64, 16, PLANE, out) == 1
+    assert list(out)[:3] == [0, 1, 2] and out[5] == 512         # A = i, W = j, C = k; 8 column groups x 2 row blocks
+    assert emul2.emul_v2_plan(200, 200, 80, 16, PLANE, out) == 1 and out[2] == 2   # no shared-memory limit any more
+    assert emul2.emul_v2_plan(512, 512, 512, 16, PLANE, out) == 0                  # 64 column groups > 16 warps
