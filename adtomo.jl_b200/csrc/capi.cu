@@ -372,10 +372,9 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
         if (pc->m == m && pc->n == n && pc->l == l) return pc;
     Plan2Cache *pc = new Plan2Cache();
     pc->m = m; pc->n = n; pc->l = l;
-    // 16 warps: two CTAs per SM (64 registers per thread); 32 warps when a row needs more column groups
+    // 12 warps: two CTAs per SM at 80 registers per thread (room for the next slot's loads in flight)
     const char *vw = getenv("ADTOMO_V2_WARPS");      // tuning aid
-    pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
-    if (!pc->ok) pc->ok = v2_build_plan(pc->plan, m, n, l, 32, 96 * 1024);
+    pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 12, 64 * 1024);
     pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
     c->plans2.push_back(pc);
     return pc;
@@ -405,21 +404,23 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     LAUNCHED(c, "k2_u0_to_P");
     phase_end(c, pk);
     pk = phase_begin(c, PH_FWD);
-    if (P.NT <= 512) {
-        auto kern = k_fwd3d_v2<512, 2>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));
-        if (occ < 1) occ = 1;
-        if (c->v2_occ > 0 && occ > c->v2_occ) occ = c->v2_occ;
-        kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol, max_rounds,
-                                                                                 S, d_rounds, d_errs, where);
-    } else {
-        auto kern = k_fwd3d_v2<1024, 1>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        kern<<<std::min(S, c->num_sms), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol, max_rounds, S,
-                                                                           d_rounds, d_errs, where);
-    }
+#define V2_LAUNCH(NTMAX_, MINB_)                                                                                       \
+    do {                                                                                                               \
+        auto kern = k_fwd3d_v2<NTMAX_, MINB_>;                                                                         \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                       \
+        int occ = 1;                                                                                                   \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));                           \
+        if (occ < 1) occ = 1;                                                                                          \
+        if (c->v2_occ > 0 && occ > c->v2_occ) occ = c->v2_occ;                                                         \
+        kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol,    \
+                                                                                 max_rounds, S, d_rounds, d_errs, where); \
+    } while (0)
+    if (P.NT <= 256) V2_LAUNCH(256, 2);
+    else if (P.NT <= 320) V2_LAUNCH(320, 2);
+    else if (P.NT <= 384) V2_LAUNCH(384, 2);
+    else if (P.NT <= 512) V2_LAUNCH(512, 2);
+    else V2_LAUNCH(1024, 1);
+#undef V2_LAUNCH
     phase_end(c, pk);
     LAUNCHED(c, "k_fwd3d_v2");
     pk = phase_begin(c, PH_CONVERT);

@@ -52,8 +52,8 @@ struct Plan2 {
     int RS;              // rows per slab incl. one pad row each side = nmu + 2
     int PC;              // row pitch (>= dC+1, multiple of 4)
     int nlev;            // dA + dW + dC - 2
-    int G, R;            // column groups per row block, row blocks per step; warps = G*R
-    int NT;              // threads = 32*G*R
+    int G;               // column groups (of LC columns) per row
+    int NT;              // threads per CTA
     int WCH, PS;         // re-skew: W rows per pass, plane pitch (even)
     long long M;         // slots per field buffer = (dA+2)*RS*PC
     long long N;
@@ -117,23 +117,33 @@ EIK_HD V2Lane v2_lane_setup(const Plan2 &P, const int lane) {
     return L;
 }
 
-// One lane's node of warp slot (rb, g) at level lam of a sweep with signs (SA, SW, SC) by role.
-// OOP: rd != wr (sweep 1 of a round), else the field is updated in place; CMP: fold |new - cmp| into
-// err (sweep 8).
-template <int SA, int SW, int SC, bool OOP, bool CMP>
-EIK_HD void v2_node(const Plan2 &P, const V2Lane &L, const int lam, const int rb, const int g, const double *rd,
-                    double *wr, const double *__restrict__ fl, const double *cmp, const double h, double &err) {
+// The eight values one node update reads.  off < 0: the lane has no node in this warp slot.
+struct V2Vals {
+    double own, fv, dA, dW, dC, uA, uW, uC;
+    int off;
+};
+
+// Loads of one lane's node of warp slot (rb, g) at level lam of a sweep with signs (SA, SW, SC) by
+// role.  OOP: rd != wr (sweep 1 of a round: old values in rd, new ones in wr), else in place.
+// Separate from the arithmetic so that the kernel can issue the NEXT slot's loads before it computes
+// the current slot (all of them are level-1 / level+1 / own values: nothing this level writes).
+template <int SA, int SW, int SC, bool OOP>
+EIK_HD void v2_load(const Plan2 &P, const V2Lane &L, const int lam, const int rb, const int g, const double *rd,
+                    const double *wr, const double *__restrict__ fl, V2Vals &V) {
     const int offA = SA * P.RS * P.PC, offW = SW * P.PC, offC = SW * P.PC + SC;   // downwind (old, level+1)
     const int offRB = V2_LA * (SA * P.RS - SW) * P.PC;
     const int wq = L.wqc + lam - rb * V2_LA - SC * g * V2_LC;
+    V.off = -1;
+    V.own = V.fv = V.dA = V.dW = V.dC = V.uA = V.uW = V.uC = 0.0;
     if ((unsigned)wq >= (unsigned)P.dW || rb * V2_LA + L.la >= P.dA || g * V2_LC + L.lc >= P.dC) return;
     const int off = L.offc + rb * offRB + lam * offW + g * V2_LC;
+    V.off = off;
     const double *p = rd + off;
-    const double own = p[0];
-    const double fv = fl[off];
-    const double dA_ = p[offA];
-    const double dW_ = p[offW];
-    const double dC_ = p[offC];
+    V.own = p[0];
+    V.fv = fl[off];
+    V.dA = p[offA];
+    V.dW = p[offW];
+    V.dC = p[offC];
 #if defined(__CUDA_ARCH__)
     if ((unsigned)(wq + 2) < (unsigned)P.dW) {   // the node this pencil reaches two levels ahead, its f one level ahead
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2 * offW));
@@ -141,23 +151,37 @@ EIK_HD void v2_node(const Plan2 &P, const V2Lane &L, const int lam, const int rb
     }
 #endif
     // upwind neighbours (new values of level-1, stored one barrier ago by this CTA); OOP: they live in wr
-    const double *pu = OOP ? (const double *)wr + off : p;
-    const double uA = pu[-offA];
-    const double uW = pu[-offW];
-    const double uC = pu[-offC];
-    double a1 = eik_min(uA, dA_), a2 = eik_min(uW, dW_), a3 = eik_min(uC, dC_);
-    double res = own;
+    const double *pu = OOP ? wr + off : p;
+    V.uA = pu[-offA];
+    V.uW = pu[-offW];
+    V.uC = pu[-offC];
+}
+
+// The update itself (Eikonal3D.cpp:47-54).  CMP: fold |new - cmp| into err (sweep 8).
+template <bool OOP, bool CMP>
+EIK_HD void v2_finish(const V2Vals &V, double *wr, const double *cmp, const double h, double &err) {
+    if (V.off < 0) return;
+    double a1 = eik_min(V.uA, V.dA), a2 = eik_min(V.uW, V.dW), a3 = eik_min(V.uC, V.dC);
+    double res = V.own;
     eik_sort3(a1, a2, a3);
     bool changed = false;
-    if (a1 < own) {   // otherwise the candidate (> a1) cannot win the min: exact skip
-        const double un = eik_solve3_sorted(a1, a2, a3, fv * h, fv * fv * h * h);
-        if (un < own) { res = un; changed = true; }
+    if (a1 < V.own) {   // otherwise the candidate (> a1) cannot win the min: exact skip
+        const double un = eik_solve3_sorted(a1, a2, a3, V.fv * h, V.fv * V.fv * h * h);
+        if (un < V.own) { res = un; changed = true; }
     }
-    if (OOP || changed) wr[off] = res;
+    if (OOP || changed) wr[V.off] = res;
     if (CMP) {
-        const double dd = fabs(res - cmp[off]);
+        const double dd = fabs(res - cmp[V.off]);
         err = (err < dd) ? dd : err;
     }
+}
+
+template <int SA, int SW, int SC, bool OOP, bool CMP>
+EIK_HD void v2_node(const Plan2 &P, const V2Lane &L, const int lam, const int rb, const int g, const double *rd,
+                    double *wr, const double *__restrict__ fl, const double *cmp, const double h, double &err) {
+    V2Vals V;
+    v2_load<SA, SW, SC, OOP>(P, L, lam, rb, g, rd, wr, fl, V);
+    v2_finish<OOP, CMP>(V, wr, cmp, h, err);
 }
 
 // dispatch on the signs of sweep sw (sweeps 0 and 7 are (+,+,+) and (-,-,-) under every role assignment)
@@ -240,70 +264,98 @@ __device__ __forceinline__ void v2_sweep(const Plan2 &P, const double *rd, doubl
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         const int excl = incl - n;
-        // slot q -> (g, rb); while a slot is computed, the lines holding the NEXT slot's upwind neighbours
-        // (stored one level ago, i.e. in L2 but not in this SM's L1) are pulled into L1
+        // slot q -> (g, rb).  The loads of the warp's next slot are issued before the current slot is
+        // computed (software pipelining by hand, two value sets alternate: the values come from L2 / DRAM
+        // and a slot's arithmetic hides their latency).
 #define V2_MAP(q_, g_, rb_)                                                                           \
     do {                                                                                              \
         const unsigned m__ = __ballot_sync(0xffffffffu, excl <= (q_) && n > 0);                       \
         g_ = 31 - __clz((int)m__);                                                                    \
         rb_ = __shfl_sync(0xffffffffu, lo, g_) + (q_) - __shfl_sync(0xffffffffu, excl, g_);           \
     } while (0)
-        int q = warp, g = 0, rb = 0;
-        if (q < total) V2_MAP(q, g, rb);
-        while (q < total) {
-            const int qn = q + nw;
-            int gn = 0, rbn = 0;
-            if (qn < total) {
-                V2_MAP(qn, gn, rbn);
-                const double *pn = (OOP ? (const double *)wr : rd) + (L.offc + rbn * (V2_LA * (SA * P.RS - SW) * P.PC) + lam * (SW * P.PC) + gn * V2_LC);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pn - SA * P.RS * P.PC));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pn - SW * P.PC));
+#define V2_LOAD(q_, V_)                                                    \
+    do {                                                                   \
+        int g__, rb__;                                                     \
+        V2_MAP(q_, g__, rb__);                                             \
+        v2_load<SA, SW, SC, OOP>(P, L, lam, rb__, g__, rd, wr, fl, V_);    \
+    } while (0)
+        int q = warp;
+        if (q < total) {
+            V2Vals V0, V1;
+            V2_LOAD(q, V0);
+            for (;;) {
+                q += nw;
+                if (q < total) V2_LOAD(q, V1);
+                v2_finish<OOP, CMP>(V0, wr, cmp, h, err);
+                if (q >= total) break;
+                q += nw;
+                if (q < total) V2_LOAD(q, V0);
+                v2_finish<OOP, CMP>(V1, wr, cmp, h, err);
+                if (q >= total) break;
             }
-            v2_node<SA, SW, SC, OOP, CMP>(P, L, lam, rb, g, rd, wr, fl, cmp, h, err);
-            q = qn; g = gn; rb = rbn;
         }
+#undef V2_LOAD
 #undef V2_MAP
         __syncthreads();
     }
 }
 
-// Re-skew of a whole field: slab by slab, chunk by chunk; two barriers per chunk.  A warp takes
-// virtual rows v = warp, warp+nw, ..., four at a time (four loads in flight before the first store).
+// Re-skew of a whole field: slab by slab, chunk by chunk; two barriers per chunk.  Lane = column C,
+// a warp takes virtual rows v = warp, warp+nw, ...: plane slot and slab offset advance by constants
+// (with a wrap), four elements are in flight per thread.  Same map as v2_reskew_index.
+template <int PHASE>
+__device__ __forceinline__ void v2_reskew_pass(const Plan2 &P, const double *s, double *d, const int sigma,
+                                               double *plane, const int w0, const int wc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int dpl = nw * P.PS, dgo = nw * P.PC, wpl = wc * P.PS, wgo = wc * P.PC;
+    for (int C = lane; C < P.dC; C += 32) {
+        const int cc = sigma > 0 ? C : P.dC - 1 - C;
+        int Wl = warp - cc;
+        while (Wl < 0) Wl += wc;
+        int pl = Wl * P.PS + C, go = (w0 + Wl + cc + 1) * P.PC + C;
+        for (int v = warp; v < wc; v += 4 * nw) {
+            int pl0, pl1, pl2, pl3, go0, go1, go2, go3;
+#define V2_STEP(pl_, go_)                                          \
+    pl_ = pl; go_ = go;                                            \
+    Wl += nw; pl += dpl; go += dgo;                                \
+    while (Wl >= wc) { Wl -= wc; pl -= wpl; go -= wgo; }
+            V2_STEP(pl0, go0) V2_STEP(pl1, go1) V2_STEP(pl2, go2) V2_STEP(pl3, go3)
+#undef V2_STEP
+            const bool b1 = v + nw < wc, b2 = v + 2 * nw < wc, b3 = v + 3 * nw < wc;
+            double x0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+            if (PHASE == 0) {
+                x0 = s[go0];
+                if (b1) x1 = s[go1];
+                if (b2) x2 = s[go2];
+                if (b3) x3 = s[go3];
+                plane[pl0] = x0;
+                if (b1) plane[pl1] = x1;
+                if (b2) plane[pl2] = x2;
+                if (b3) plane[pl3] = x3;
+            } else {
+                x0 = plane[pl0];
+                if (b1) x1 = plane[pl1];
+                if (b2) x2 = plane[pl2];
+                if (b3) x3 = plane[pl3];
+                d[go0] = x0;
+                if (b1) d[go1] = x1;
+                if (b2) d[go2] = x2;
+                if (b3) d[go3] = x3;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void v2_reskew(const Plan2 &P, const double *src, double *dst, const int sigmaFrom,
                                           double *plane) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int A = 0; A < P.dA; A++) {
         const double *s = src + (long long)(A + 1) * P.RS * P.PC;
         double *d = dst + (long long)(A + 1) * P.RS * P.PC;
         for (int w0 = 0; w0 < P.dW; w0 += P.WCH) {
             const int wc = (P.dW - w0 < P.WCH) ? P.dW - w0 : P.WCH;
-            for (int C = lane; C < P.dC; C += 32) {
-                for (int v = warp; v < wc; v += 4 * nw) {
-                    int pl[4], go[4];
-                    double x[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int vj = (v + j * nw < wc) ? v + j * nw : v;     // clamp: duplicates rewrite the same value
-                        v2_reskew_index(P, sigmaFrom, w0, wc, vj, C, pl[j], go[j]);
-                        x[j] = s[go[j]];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) plane[pl[j]] = x[j];
-                }
-            }
+            v2_reskew_pass<0>(P, s, d, sigmaFrom, plane, w0, wc);
             __syncthreads();
-            for (int C = lane; C < P.dC; C += 32) {
-                for (int v = warp; v < wc; v += 4 * nw) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (v + j * nw < wc) {
-                            int pl, go;
-                            v2_reskew_index(P, -sigmaFrom, w0, wc, v + j * nw, C, pl, go);
-                            d[go] = plane[pl];
-                        }
-                    }
-                }
-            }
+            v2_reskew_pass<1>(P, s, d, -sigmaFrom, plane, w0, wc);
             __syncthreads();
         }
     }
@@ -408,11 +460,11 @@ __global__ void k2_P_to_rowmajor(const Plan2 P, const double *__restrict__ bufs,
 // ---------------------------------------------------------------------------------------------
 // host: plan construction
 // ---------------------------------------------------------------------------------------------
-// Chooses the axis roles (A, W, C) for an m x n x l grid: lanes fill best when dC is a multiple of 8,
-// a warp is live for dW + 10 levels of which dW are fully used, and role assignments with A = k need 6
-// instead of 4 layout changes per round.  max_warps: warps per CTA (16: two CTAs per SM at 64 registers).
-// Returns false when the grid cannot be handled (column groups exceed the warps, 32-bit slots).
-inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int max_warps, size_t plane_bytes) {
+// Chooses the axis roles (A, W, C) for an m x n x l grid: lanes fill best when dC is a multiple of 8
+// and dA of 4, a warp slot is live for dW + 10 levels of which dW are fully used, and role assignments
+// with A = k need 6 instead of 4 layout changes per round.  nwarps: warps per CTA.
+// Returns false when the grid cannot be handled (more than 32 column groups, 32-bit slots).
+inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plane_bytes) {
     static const int SG[8][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, -1, 1}, {1, -1, 1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, -1}};
     const int ext[3] = {m, n, l};
     double best = -1.0;
@@ -421,7 +473,7 @@ inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int max_warps, size_t p
     for (int p = 0; p < 6; p++) {
         const int dA = ext[perms[p][0]], dW = ext[perms[p][1]], dC = ext[perms[p][2]];
         const int G = (dC + V2_LC - 1) / V2_LC;
-        if (G > max_warps) continue;
+        if (G > 32) continue;      // lane g of a warp computes the window of column group g
         // layout changes per round (sigma = sW*sC along the reference's sweep order, cyclic)
         int changes = 0;
         for (int s = 0; s < 8; s++) {
@@ -432,12 +484,8 @@ inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int max_warps, size_t p
         const double fill = (double)dC / (V2_LC * G);
         const double live = (double)dW / (dW + V2_LC + V2_LA - 2);
         const int nrb = (dA + V2_LA - 1) / V2_LA;
-        int R = max_warps / G;
-        if (R > nrb) R = nrb;
-        const double rowfill = (double)nrb / (((nrb + R - 1) / R) * R);   // idle warps when few row blocks
         const double afill = (double)dA / (nrb * V2_LA);
-        const double warps = (double)(G * R) / max_warps;                 // unused warp slots
-        double score = fill * live * rowfill * afill * (0.5 + 0.5 * warps) * (1.0 - 0.012 * changes);
+        double score = fill * live * afill * (1.0 - 0.02 * changes);
         if (perms[p][2] == 2) score *= 1.01;      // tie-break: lanes along the grid's fastest axis
         if (score > best) { best = score; for (int q = 0; q < 3; q++) bestRole[q] = perms[p][q]; }
     }
@@ -449,10 +497,7 @@ inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int max_warps, size_t p
     P.PC = ((P.dC + 1 + 3) / 4) * 4;
     P.nlev = P.dA + P.dW + P.dC - 2;
     P.G = (P.dC + V2_LC - 1) / V2_LC;
-    P.R = max_warps / P.G;
-    const int nrb = (P.dA + V2_LA - 1) / V2_LA;
-    if (P.R > nrb) P.R = nrb;
-    P.NT = 32 * P.G * P.R;
+    P.NT = 32 * nwarps;
     P.PS = (P.dC + 1) & ~1;
     P.WCH = (int)(plane_bytes / (sizeof(double) * P.PS));
     if (P.WCH > P.dW) P.WCH = P.dW;

@@ -50,7 +50,7 @@ extern "C" int emul_v2_plan(int m, int n, int l, int max_warps, long long plane_
     Plan2 P;
     if (!v2_build_plan(P, m, n, l, max_warps, (size_t)plane_bytes)) return 0;
     out[0] = P.role[0]; out[1] = P.role[1]; out[2] = P.role[2];
-    out[3] = P.G; out[4] = P.R; out[5] = P.NT; out[6] = P.WCH;
+    out[3] = P.G; out[4] = 0; out[5] = P.NT; out[6] = P.WCH;
     return 1;
 }
 

@@ -110,6 +110,6 @@ def test_emulated_v2_bitexact(emul2, oracle, dims, tol, warps, plane):
 def test_v2_plan_roles(emul2):
     out = (ctypes.c_int * 7)()
     assert emul2.emul_v2_plan(128, 128, 64, 16, PLANE, out) == 1
-    assert list(out)[:3] == [0, 1, 2] and out[5] == 512         # A = i, W = j, C = k; 8 column groups x 2 row blocks
+    assert list(out)[:3] == [0, 1, 2] and out[5] == 512         # A = i, W = j, C = k
     assert emul2.emul_v2_plan(200, 200, 80, 16, PLANE, out) == 1 and out[2] == 2   # no shared-memory limit any more
-    assert emul2.emul_v2_plan(512, 512, 512, 16, PLANE, out) == 0                  # 64 column groups > 16 warps
+    assert emul2.emul_v2_plan(512, 512, 512, 16, PLANE, out) == 0                  # 64 column groups > 32 lanes
