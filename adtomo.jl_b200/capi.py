@@ -68,6 +68,8 @@ def load_library():
     L.adtomo_last_phase_ms.argtypes = [_vp, c_int]
     L.adtomo_launch_count.restype = ctypes.c_longlong
     L.adtomo_launch_count.argtypes = [_vp]
+    L.adtomo_selftest_sqrt.restype = c_int
+    L.adtomo_selftest_sqrt.argtypes = [_vp, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_longlong)]
     L.adtomo_eikonal2d_forward.restype = c_int
     L.adtomo_eikonal2d_forward.argtypes = [_vp, _vp, c_int, c_int, c_double, c_int, c_int]
     L.adtomo_eikonal2d_backward.restype = c_int
@@ -164,6 +166,14 @@ class Context:
     @property
     def launch_count(self):
         return int(self._lib.adtomo_launch_count(self.handle))
+
+    def selftest_sqrt(self, n, seed=1):
+        """Mismatches of the library's call-free fp64 sqrt against CUDA's sqrt on n arguments (must be 0)."""
+        bad = ctypes.c_longlong(-1)
+        rc = self._lib.adtomo_selftest_sqrt(self.handle, int(n), int(seed), ctypes.byref(bad))
+        if rc < 0:
+            raise AdtomoError(f"adtomo_selftest_sqrt: rc={rc}: {self._lib.adtomo_last_error().decode()}")
+        return int(bad.value)
 
     # ---- NCCL (one all-reduce of the packed [grad | misfit] buffer per evaluation) -------------
     @staticmethod

@@ -236,6 +236,48 @@ static int check_launch(adtomo_ctx *c, const char *what) {
         if (rc__) return rc__;                \
     } while (0)
 
+// ---------------------------------------------------------------------------------------
+// self-test of the call-free device sqrt (eik_core.h): bit-for-bit against the CUDA library's sqrt
+// ---------------------------------------------------------------------------------------
+__global__ void k_selftest_sqrt(const long long n, const unsigned long long seed, unsigned long long *bad) {
+    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < n; id += (long long)gridDim.x * blockDim.x) {
+        // splitmix64
+        unsigned long long z = seed + 0x9e3779b97f4a7c15ULL * (unsigned long long)(id + 1);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        z ^= z >> 31;
+        double x;
+        const int kind = (int)(id & 7);
+        if (kind < 3) x = __longlong_as_double((long long)z);                                   // any bit pattern
+        else if (kind < 6) x = __longlong_as_double((long long)((z & 0x000fffffffffffffULL) |     // exponents around 1
+                                                    ((0x3f0ULL + ((z >> 52) & 0x1f)) << 52)));
+        else if (kind == 6) x = __longlong_as_double((long long)(z & 0x001fffffffffffffULL));    // subnormal / tiny
+        else {
+            const double sp[8] = {0.0, -0.0, 1.0, 4.0, __longlong_as_double(0x7ff0000000000000LL),
+                                  __longlong_as_double(0xfff0000000000000LL), __longlong_as_double(0x7ff8000000000000LL), -1.0};
+            x = sp[(id >> 3) & 7];
+        }
+        const double a = eik_sqrt(x), b = sqrt(x);
+        const bool same = (__double_as_longlong(a) == __double_as_longlong(b)) || (a != a && b != b);
+        if (!same) atomicAdd(bad, 1ULL);
+    }
+}
+
+extern "C" int adtomo_selftest_sqrt(adtomo_ctx *c, long long n, unsigned long long seed, long long *mismatches) {
+    if (!c || !mismatches) return fail(ADTOMO_ERR_ARG, "adtomo_selftest_sqrt: null argument");
+    CK(cudaSetDevice(c->device));
+    unsigned long long *d;
+    WS(c, "selftest", unsigned long long, 1, d);
+    CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->stream));
+    k_selftest_sqrt<<<c->num_sms * 8, 256, 0, c->stream>>>(n, seed, d);
+    LAUNCHED(c, "k_selftest_sqrt");
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *mismatches = (long long)h;
+    return 0;
+}
+
 // device pointer for an input: either the caller's (DEVICE) or a staged copy (HOST)
 template <typename T>
 static int stage_in(adtomo_ctx *c, const char *name, const T *src, size_t count, int loc, const T **out) {

@@ -157,23 +157,45 @@ EIK_HD void v2_load(const Plan2 &P, const V2Lane &L, const int lam, const int rb
     V.uC = pu[-offC];
 }
 
-// The update itself (Eikonal3D.cpp:47-54).  CMP: fold |new - cmp| into err (sweep 8).
+// The update itself (Eikonal3D.cpp:47-54), in two steps so that the kernel can issue the next slot's
+// loads in between: v2_prep consumes the eight loaded values (per-axis minima, sorted), v2_solve does
+// the arithmetic and the store.  CMP: fold |new - cmp| into err (sweep 8).
+struct V2Prep {
+    double a1, a2, a3, own, fv;
+    int off;
+};
+
+EIK_HD void v2_prep(const V2Vals &V, V2Prep &Q) {
+    Q.off = V.off;
+    Q.own = V.own;
+    Q.fv = V.fv;
+    Q.a1 = eik_min(V.uA, V.dA);
+    Q.a2 = eik_min(V.uW, V.dW);
+    Q.a3 = eik_min(V.uC, V.dC);
+    eik_sort3(Q.a1, Q.a2, Q.a3);
+}
+
 template <bool OOP, bool CMP>
-EIK_HD void v2_finish(const V2Vals &V, double *wr, const double *cmp, const double h, double &err) {
-    if (V.off < 0) return;
-    double a1 = eik_min(V.uA, V.dA), a2 = eik_min(V.uW, V.dW), a3 = eik_min(V.uC, V.dC);
-    double res = V.own;
-    eik_sort3(a1, a2, a3);
+EIK_HD void v2_solve(const V2Prep &Q, double *wr, const double *cmp, const double h, double &err) {
+    if (Q.off < 0) return;
+    double res = Q.own;
     bool changed = false;
-    if (a1 < V.own) {   // otherwise the candidate (> a1) cannot win the min: exact skip
-        const double un = eik_solve3_sorted(a1, a2, a3, V.fv * h, V.fv * V.fv * h * h);
-        if (un < V.own) { res = un; changed = true; }
+    if (Q.a1 < Q.own) {   // otherwise the candidate (> a1) cannot win the min: exact skip
+        const double un = eik_solve3_sorted(Q.a1, Q.a2, Q.a3, Q.fv * h, Q.fv * Q.fv * h * h);
+        if (un < Q.own) { res = un; changed = true; }
     }
-    if (OOP || changed) wr[V.off] = res;
+    if (OOP || changed) wr[Q.off] = res;
     if (CMP) {
-        const double dd = fabs(res - cmp[V.off]);
+        const double dd = fabs(res - cmp[Q.off]);
         err = (err < dd) ? dd : err;
     }
+}
+
+template <bool OOP, bool CMP>
+EIK_HD void v2_finish(const V2Vals &V, double *wr, const double *cmp, const double h, double &err) {
+    V2Prep Q;
+    v2_prep(V, Q);
+    v2_solve<OOP, CMP>(Q, wr, cmp, h, err);
 }
 
 template <int SA, int SW, int SC, bool OOP, bool CMP>
@@ -264,9 +286,9 @@ __device__ __forceinline__ void v2_sweep(const Plan2 &P, const double *rd, doubl
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         const int excl = incl - n;
-        // slot q -> (g, rb).  The loads of the warp's next slot are issued before the current slot is
-        // computed (software pipelining by hand, two value sets alternate: the values come from L2 / DRAM
-        // and a slot's arithmetic hides their latency).
+        // slot q -> (g, rb).  The loads of the warp's next slot are issued before the current slot's
+        // arithmetic (software pipelining by hand: the values come from L2 / DRAM and the ~120 instructions
+        // of the solve hide their latency).
 #define V2_MAP(q_, g_, rb_)                                                                           \
     do {                                                                                              \
         const unsigned m__ = __ballot_sync(0xffffffffu, excl <= (q_) && n > 0);                       \
@@ -281,16 +303,15 @@ __device__ __forceinline__ void v2_sweep(const Plan2 &P, const double *rd, doubl
     } while (0)
         int q = warp;
         if (q < total) {
-            V2Vals V0, V1;
-            V2_LOAD(q, V0);
+            V2Vals V;
+            V2_LOAD(q, V);
+#pragma unroll 1
             for (;;) {
+                V2Prep Q;
+                v2_prep(V, Q);                     // consumes V: its registers take the next slot's loads
                 q += nw;
-                if (q < total) V2_LOAD(q, V1);
-                v2_finish<OOP, CMP>(V0, wr, cmp, h, err);
-                if (q >= total) break;
-                q += nw;
-                if (q < total) V2_LOAD(q, V0);
-                v2_finish<OOP, CMP>(V1, wr, cmp, h, err);
+                if (q < total) V2_LOAD(q, V);
+                v2_solve<OOP, CMP>(Q, wr, cmp, h, err);
                 if (q >= total) break;
             }
         }
@@ -306,6 +327,7 @@ __device__ __forceinline__ void v2_sweep(const Plan2 &P, const double *rd, doubl
 template <int PHASE>
 __device__ __forceinline__ void v2_reskew_pass(const Plan2 &P, const double *s, double *d, const int sigma,
                                                double *plane, const int w0, const int wc) {
+    constexpr int U = 8;                  // elements in flight per thread (the loads come from DRAM)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int dpl = nw * P.PS, dgo = nw * P.PC, wpl = wc * P.PS, wgo = wc * P.PC;
     for (int C = lane; C < P.dC; C += 32) {
@@ -313,35 +335,26 @@ __device__ __forceinline__ void v2_reskew_pass(const Plan2 &P, const double *s, 
         int Wl = warp - cc;
         while (Wl < 0) Wl += wc;
         int pl = Wl * P.PS + C, go = (w0 + Wl + cc + 1) * P.PC + C;
-        for (int v = warp; v < wc; v += 4 * nw) {
-            int pl0, pl1, pl2, pl3, go0, go1, go2, go3;
-#define V2_STEP(pl_, go_)                                          \
-    pl_ = pl; go_ = go;                                            \
-    Wl += nw; pl += dpl; go += dgo;                                \
-    while (Wl >= wc) { Wl -= wc; pl -= wpl; go -= wgo; }
-            V2_STEP(pl0, go0) V2_STEP(pl1, go1) V2_STEP(pl2, go2) V2_STEP(pl3, go3)
-#undef V2_STEP
-            const bool b1 = v + nw < wc, b2 = v + 2 * nw < wc, b3 = v + 3 * nw < wc;
-            double x0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-            if (PHASE == 0) {
-                x0 = s[go0];
-                if (b1) x1 = s[go1];
-                if (b2) x2 = s[go2];
-                if (b3) x3 = s[go3];
-                plane[pl0] = x0;
-                if (b1) plane[pl1] = x1;
-                if (b2) plane[pl2] = x2;
-                if (b3) plane[pl3] = x3;
-            } else {
-                x0 = plane[pl0];
-                if (b1) x1 = plane[pl1];
-                if (b2) x2 = plane[pl2];
-                if (b3) x3 = plane[pl3];
-                d[go0] = x0;
-                if (b1) d[go1] = x1;
-                if (b2) d[go2] = x2;
-                if (b3) d[go3] = x3;
+        for (int v = warp; v < wc; v += U * nw) {
+            int pls[U], gos[U];
+            double x[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                pls[j] = pl; gos[j] = go;
+                Wl += nw; pl += dpl; go += dgo;
+                while (Wl >= wc) { Wl -= wc; pl -= wpl; go -= wgo; }
             }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                x[j] = 0.0;
+                if (v + j * nw < wc) x[j] = PHASE == 0 ? s[gos[j]] : plane[pls[j]];
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                if (v + j * nw < wc) {
+                    if (PHASE == 0) plane[pls[j]] = x[j];
+                    else d[gos[j]] = x[j];
+                }
         }
     }
 }

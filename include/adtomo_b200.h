@@ -62,6 +62,9 @@ double adtomo_last_kernel_ms(adtomo_ctx *ctx);
 double adtomo_last_phase_ms(adtomo_ctx *ctx, int phase);
 /* Number of kernels this library has launched on the context since creation. */
 long long adtomo_launch_count(adtomo_ctx *ctx);
+/* Self-test: the library's call-free fp64 square root (csrc/eik_core.h) against the CUDA math library's
+   correctly rounded sqrt on n pseudo-random and special arguments; *mismatches must come back 0. */
+int adtomo_selftest_sqrt(adtomo_ctx *ctx, long long n, unsigned long long seed, long long *mismatches);
 
 /* ---- 1:1 replacements, host pointers, use an internal per-thread default context -------- */
 /* forward(u,f,m,n,h,ix,jx)           deps/CustomOps/Eikonal/Eikonal.h:54-93 */
