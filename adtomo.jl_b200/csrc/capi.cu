@@ -58,6 +58,7 @@ struct adtomo_ctx {
     int force_cluster = 0;                      // testing aid: ADTOMO_FORCE_CLUSTER=2|4|8 splits every source over a cluster
     int force_v0 = 0;                           // debugging aid: ADTOMO_FORCE_V0=1 selects the row-major kernel
     int force_v1 = 0;                           // debugging aid: ADTOMO_FORCE_V1=1 selects the level-major kernel
+    int force_v2 = 0;                           // debugging aid: ADTOMO_FORCE_V2=1 selects the skewed-pencil kernel for any batch
     int v2_occ = 0;                             // tuning aid: ADTOMO_V2_OCC caps the CTAs per SM of the skewed-pencil kernel
     std::vector<struct Plan2Cache *> plans2;    // skewed-pencil plans, one per grid shape
     // the +inf padding of the skewed-pencil field buffers is written once per (buffer, plan, sources)
@@ -156,6 +157,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     c->force_v0 = (fv0 && fv0[0] == '1');
     const char *fv1 = getenv("ADTOMO_FORCE_V1");
     c->force_v1 = (fv1 && fv1[0] == '1');
+    const char *fv2 = getenv("ADTOMO_FORCE_V2");
+    c->force_v2 = (fv2 && fv2[0] == '1');
     const char *vocc = getenv("ADTOMO_V2_OCC");
     c->v2_occ = vocc ? atoi(vocc) : 0;
     const char *fvv = getenv("ADTOMO_FWD_VARIANT");
@@ -414,9 +417,9 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
         if (pc->m == m && pc->n == n && pc->l == l) return pc;
     Plan2Cache *pc = new Plan2Cache();
     pc->m = m; pc->n = n; pc->l = l;
-    // 12 warps: two CTAs per SM at 80 registers per thread (room for the next slot's loads in flight)
+    // 16 warps: two CTAs per SM at 64 registers per thread
     const char *vw = getenv("ADTOMO_V2_WARPS");      // tuning aid
-    pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 12, 64 * 1024);
+    pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
     pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
     c->plans2.push_back(pc);
     return pc;
@@ -475,16 +478,22 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
 // dU: S x N row-major, holds u0 on entry and the travel times on exit.
 static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3 &d, double h, double tol,
                         int max_rounds, int S, int *d_rounds, double *d_errs) {
-    if (!c->force_v0 && !c->force_v1 && !c->force_cluster) {
-        const Plan2Cache *p2 = get_plan2(c, d.m, d.n, d.l);
-        if (p2->ok) return fwd3d_v2(c, p2, dU, df, d, h, tol, max_rounds, S, d_rounds, d_errs);
-    }
     PlanCache *pc = nullptr;
     int rc = get_plan(c, d.m, d.n, d.l, &pc);
     if (rc) return rc;
     FwdCfg cfg;
     bool fits = false;
     for (int cs = std::max(1, c->force_cluster); cs <= 8 && !fits; cs *= 2) fits = fwd_config(pc, cs, &cfg);
+    // Kernel choice.  Few sources (every source gets its own SM or cluster of SMs in ONE wave): the
+    // level-major kernel, which puts 1024 threads (x cluster size) on a source.  A batch that oversubscribes
+    // the SMs: the skewed-pencil kernel (two sources per SM, no shared-memory limit on the grid size).
+    if (!c->force_v0 && !c->force_v1 && !c->force_cluster) {
+        const bool few = fits && (long long)S * cfg.CS <= c->num_sms;
+        if (!few || c->force_v2) {
+            const Plan2Cache *p2 = get_plan2(c, d.m, d.n, d.l);
+            if (p2->ok) return fwd3d_v2(c, p2, dU, df, d, h, tol, max_rounds, S, d_rounds, d_errs);
+        }
+    }
     if (!c->force_v0 && fits) {
         // level-major path: convert in, sweep, convert out
         double *bufs, *flay, *errPart;

@@ -120,6 +120,7 @@ EIK_HD V2Lane v2_lane_setup(const Plan2 &P, const int lane) {
 // The eight values one node update reads.  off < 0: the lane has no node in this warp slot.
 struct V2Vals {
     double own, fv, dA, dW, dC, uA, uW, uC;
+    double ref;   // CMP sweeps: the round-start value of the node
     int off;
 };
 
@@ -127,14 +128,14 @@ struct V2Vals {
 // role.  OOP: rd != wr (sweep 1 of a round: old values in rd, new ones in wr), else in place.
 // Separate from the arithmetic so that the kernel can issue the NEXT slot's loads before it computes
 // the current slot (all of them are level-1 / level+1 / own values: nothing this level writes).
-template <int SA, int SW, int SC, bool OOP>
+template <int SA, int SW, int SC, bool OOP, bool CMP>
 EIK_HD void v2_load(const Plan2 &P, const V2Lane &L, const int lam, const int rb, const int g, const double *rd,
-                    const double *wr, const double *__restrict__ fl, V2Vals &V) {
+                    const double *wr, const double *__restrict__ fl, const double *cmp, V2Vals &V) {
     const int offA = SA * P.RS * P.PC, offW = SW * P.PC, offC = SW * P.PC + SC;   // downwind (old, level+1)
     const int offRB = V2_LA * (SA * P.RS - SW) * P.PC;
     const int wq = L.wqc + lam - rb * V2_LA - SC * g * V2_LC;
     V.off = -1;
-    V.own = V.fv = V.dA = V.dW = V.dC = V.uA = V.uW = V.uC = 0.0;
+    V.own = V.fv = V.dA = V.dW = V.dC = V.uA = V.uW = V.uC = V.ref = 0.0;
     if ((unsigned)wq >= (unsigned)P.dW || rb * V2_LA + L.la >= P.dA || g * V2_LC + L.lc >= P.dC) return;
     const int off = L.offc + rb * offRB + lam * offW + g * V2_LC;
     V.off = off;
@@ -155,13 +156,14 @@ EIK_HD void v2_load(const Plan2 &P, const V2Lane &L, const int lam, const int rb
     V.uA = pu[-offA];
     V.uW = pu[-offW];
     V.uC = pu[-offC];
+    if (CMP) V.ref = cmp[off];
 }
 
 // The update itself (Eikonal3D.cpp:47-54), in two steps so that the kernel can issue the next slot's
 // loads in between: v2_prep consumes the eight loaded values (per-axis minima, sorted), v2_solve does
 // the arithmetic and the store.  CMP: fold |new - cmp| into err (sweep 8).
 struct V2Prep {
-    double a1, a2, a3, own, fv;
+    double a1, a2, a3, own, fv, ref;
     int off;
 };
 
@@ -169,6 +171,7 @@ EIK_HD void v2_prep(const V2Vals &V, V2Prep &Q) {
     Q.off = V.off;
     Q.own = V.own;
     Q.fv = V.fv;
+    Q.ref = V.ref;
     Q.a1 = eik_min(V.uA, V.dA);
     Q.a2 = eik_min(V.uW, V.dW);
     Q.a3 = eik_min(V.uC, V.dC);
@@ -176,7 +179,7 @@ EIK_HD void v2_prep(const V2Vals &V, V2Prep &Q) {
 }
 
 template <bool OOP, bool CMP>
-EIK_HD void v2_solve(const V2Prep &Q, double *wr, const double *cmp, const double h, double &err) {
+EIK_HD void v2_solve(const V2Prep &Q, double *wr, const double h, double &err) {
     if (Q.off < 0) return;
     double res = Q.own;
     bool changed = false;
@@ -186,24 +189,24 @@ EIK_HD void v2_solve(const V2Prep &Q, double *wr, const double *cmp, const doubl
     }
     if (OOP || changed) wr[Q.off] = res;
     if (CMP) {
-        const double dd = fabs(res - cmp[Q.off]);
+        const double dd = fabs(res - Q.ref);
         err = (err < dd) ? dd : err;
     }
 }
 
 template <bool OOP, bool CMP>
-EIK_HD void v2_finish(const V2Vals &V, double *wr, const double *cmp, const double h, double &err) {
+EIK_HD void v2_finish(const V2Vals &V, double *wr, const double h, double &err) {
     V2Prep Q;
     v2_prep(V, Q);
-    v2_solve<OOP, CMP>(Q, wr, cmp, h, err);
+    v2_solve<OOP, CMP>(Q, wr, h, err);
 }
 
 template <int SA, int SW, int SC, bool OOP, bool CMP>
 EIK_HD void v2_node(const Plan2 &P, const V2Lane &L, const int lam, const int rb, const int g, const double *rd,
                     double *wr, const double *__restrict__ fl, const double *cmp, const double h, double &err) {
     V2Vals V;
-    v2_load<SA, SW, SC, OOP>(P, L, lam, rb, g, rd, wr, fl, V);
-    v2_finish<OOP, CMP>(V, wr, cmp, h, err);
+    v2_load<SA, SW, SC, OOP, CMP>(P, L, lam, rb, g, rd, wr, fl, cmp, V);
+    v2_finish<OOP, CMP>(V, wr, h, err);
 }
 
 // dispatch on the signs of sweep sw (sweeps 0 and 7 are (+,+,+) and (-,-,-) under every role assignment)
@@ -299,7 +302,7 @@ __device__ __forceinline__ void v2_sweep(const Plan2 &P, const double *rd, doubl
     do {                                                                   \
         int g__, rb__;                                                     \
         V2_MAP(q_, g__, rb__);                                             \
-        v2_load<SA, SW, SC, OOP>(P, L, lam, rb__, g__, rd, wr, fl, V_);    \
+        v2_load<SA, SW, SC, OOP, CMP>(P, L, lam, rb__, g__, rd, wr, fl, cmp, V_); \
     } while (0)
         int q = warp;
         if (q < total) {
@@ -311,7 +314,7 @@ __device__ __forceinline__ void v2_sweep(const Plan2 &P, const double *rd, doubl
                 v2_prep(V, Q);                     // consumes V: its registers take the next slot's loads
                 q += nw;
                 if (q < total) V2_LOAD(q, V);
-                v2_solve<OOP, CMP>(Q, wr, cmp, h, err);
+                v2_solve<OOP, CMP>(Q, wr, h, err);
                 if (q >= total) break;
             }
         }
