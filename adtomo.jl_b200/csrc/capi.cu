@@ -420,6 +420,8 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
     // 16 warps: two CTAs per SM at 64 registers per thread
     const char *vw = getenv("ADTOMO_V2_WARPS");      // tuning aid
     pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
+    const char *vpf = getenv("ADTOMO_V2_PF");         // tuning aid
+    if (vpf) pc->plan.pf = atoi(vpf);
     pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
     c->plans2.push_back(pc);
     return pc;
@@ -566,12 +568,24 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
         k_adj3d_count2<<<eg, 256, 0, c->stream>>>(code, CM, cnt, Q, cnts + S, d, S);
         phase_end(c, pk);
         LAUNCHED(c, "k_adj3d_count2");
-        int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo2<1024>, 1024, 0));
-        if (occ < 1) occ = 1;
-        int grid = std::min(S, c->num_sms * occ);
+        // 1024 threads per source, one source per SM at a time.  (Measured on the 256-source bench batch: 512-thread
+        // CTAs at 2-3 per SM 38.8 ms, 256-thread CTAs 42.4 ms, against 35.0 ms: a wave of the ready queue is short
+        // and the per-wave barrier cost falls with the number of threads that share it.)  ADTOMO_ADJ_NT: tuning aid.
+        static const int adj_nt_env = getenv("ADTOMO_ADJ_NT") ? atoi(getenv("ADTOMO_ADJ_NT")) : 0;
+        const int adj_nt = adj_nt_env ? adj_nt_env : 1024;
         pk = phase_begin(c, PH_ADJ_SWEEP);
-        k_adj3d_topo2<1024><<<grid, 1024, 0, c->stream>>>(UX, GD, CM, (unsigned int *)cnt, Q, cnts + S, cnts, d, S, d_status);
+#define ADJ_LAUNCH(NT_)                                                                                               \
+    do {                                                                                                              \
+        int occ = 1;                                                                                                  \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo2<NT_>, NT_, 0));                          \
+        if (occ < 1) occ = 1;                                                                                         \
+        const int grid = std::min(S, c->num_sms * occ);                                                               \
+        k_adj3d_topo2<NT_><<<grid, NT_, 0, c->stream>>>(UX, GD, CM, (unsigned int *)cnt, Q, cnts + S, cnts, d, S, d_status); \
+    } while (0)
+        if (adj_nt <= 256) ADJ_LAUNCH(256);
+        else if (adj_nt <= 512) ADJ_LAUNCH(512);
+        else ADJ_LAUNCH(1024);
+#undef ADJ_LAUNCH
         phase_end(c, pk);
         LAUNCHED(c, "k_adj3d_topo2");
         pk = phase_begin(c, PH_ADJ_FINISH);

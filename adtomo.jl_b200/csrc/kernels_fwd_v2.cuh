@@ -55,6 +55,7 @@ struct Plan2 {
     int G;               // column groups (of LC columns) per row
     int NT;              // threads per CTA
     int WCH, PS;         // re-skew: W rows per pass, plane pitch (even)
+    int pf;              // prefetch two levels ahead into L1 (tuning switch; no measurable effect once the loads are pipelined)
     long long M;         // slots per field buffer = (dA+2)*RS*PC
     long long N;
     int sg[8][3];        // (sA, sW, sC) of the reference's 8 sweeps (Eikonal3D.cpp:59-68) by role
@@ -146,7 +147,7 @@ EIK_HD void v2_load(const Plan2 &P, const V2Lane &L, const int lam, const int rb
     V.dW = p[offW];
     V.dC = p[offC];
 #if defined(__CUDA_ARCH__)
-    if ((unsigned)(wq + 2) < (unsigned)P.dW) {   // the node this pencil reaches two levels ahead, its f one level ahead
+    if (P.pf && (unsigned)(wq + 2) < (unsigned)P.dW) {   // the node this pencil reaches two levels ahead, its f one level ahead
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2 * offW));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(fl + off + offW));
     }
@@ -284,11 +285,13 @@ __device__ __forceinline__ void v2_sweep(const Plan2 &P, const double *rd, doubl
         int incl = n;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
+            if (d >= P.G) break;                   // groups live in lanes 0..G-1 (uniform exit)
             const int t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int total = __shfl_sync(0xffffffffu, incl, P.G - 1);
         const int excl = incl - n;
+        const int rb0 = lo - excl;                 // slot q of group g is row block rb0[g] + q
         // slot q -> (g, rb).  The loads of the warp's next slot are issued before the current slot's
         // arithmetic (software pipelining by hand: the values come from L2 / DRAM and the ~120 instructions
         // of the solve hide their latency).
@@ -296,7 +299,7 @@ __device__ __forceinline__ void v2_sweep(const Plan2 &P, const double *rd, doubl
     do {                                                                                              \
         const unsigned m__ = __ballot_sync(0xffffffffu, excl <= (q_) && n > 0);                       \
         g_ = 31 - __clz((int)m__);                                                                    \
-        rb_ = __shfl_sync(0xffffffffu, lo, g_) + (q_) - __shfl_sync(0xffffffffu, excl, g_);           \
+        rb_ = __shfl_sync(0xffffffffu, rb0, g_) + (q_);                                               \
     } while (0)
 #define V2_LOAD(q_, V_)                                                    \
     do {                                                                   \
@@ -514,6 +517,7 @@ inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plan
     P.nlev = P.dA + P.dW + P.dC - 2;
     P.G = (P.dC + V2_LC - 1) / V2_LC;
     P.NT = 32 * nwarps;
+    P.pf = 0;
     P.PS = (P.dC + 1) & ~1;
     P.WCH = (int)(plane_bytes / (sizeof(double) * P.PS));
     if (P.WCH > P.dW) P.WCH = P.dW;
