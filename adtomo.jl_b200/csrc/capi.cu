@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -59,6 +60,8 @@ struct adtomo_ctx {
     int force_v0 = 0;                           // debugging aid: ADTOMO_FORCE_V0=1 selects the row-major kernel
     int force_v1 = 0;                           // debugging aid: ADTOMO_FORCE_V1=1 selects the level-major kernel
     int force_v2 = 0;                           // debugging aid: ADTOMO_FORCE_V2=1 selects the skewed-pencil kernel for any batch
+    int v2_pairing = 1;                         // tuning aid: ADTOMO_V2_PAIRING=0 keeps sources in caller order
+    std::map<std::tuple<const void *, int, const void *>, int *> v2_spent;   // rounds per source of earlier calls, per batch
     int v2_occ = 0;                             // tuning aid: ADTOMO_V2_OCC caps the CTAs per SM of the skewed-pencil kernel
     std::vector<struct Plan2Cache *> plans2;    // skewed-pencil plans, one per grid shape
     // the +inf padding of the skewed-pencil field buffers is written once per (buffer, plan, sources)
@@ -159,6 +162,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     c->force_v1 = (fv1 && fv1[0] == '1');
     const char *fv2 = getenv("ADTOMO_FORCE_V2");
     c->force_v2 = (fv2 && fv2[0] == '1');
+    const char *vpair = getenv("ADTOMO_V2_PAIRING");
+    c->v2_pairing = vpair ? atoi(vpair) : 1;
     const char *vocc = getenv("ADTOMO_V2_OCC");
     c->v2_occ = vocc ? atoi(vocc) : 0;
     const char *fvv = getenv("ADTOMO_FWD_VARIANT");
@@ -181,6 +186,7 @@ extern "C" int adtomo_destroy(adtomo_ctx *c) {
     }
     if (c->nccl_comm) adtomo_nccl_finalize(c);
     for (auto *pc : c->plans2) delete pc;
+    for (auto &kv : c->v2_spent) cudaFree(kv.second);
     for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -432,11 +438,28 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
                     double tol, int max_rounds, int S, int *d_rounds, double *d_errs) {
     const Plan2 &P = pc->plan;
     double *bufs, *flay;
-    int *where;
+    int *where, *order, *spent;
     const size_t nb = (size_t)S * 3 * P.M;
     WS(c, "fwd2_bufs", double, nb, bufs);
     WS(c, "fwd2_flay", double, (size_t)2 * P.M, flay);
-    WS(c, "fwd2_where", int, S, where);
+    WS(c, "fwd2_where", int, 2 * (size_t)S, where);
+    order = where + S;
+    // rounds each source of THIS batch needed last time (batch = plan, size, caller's rounds array)
+    {
+        const auto key = std::make_tuple((const void *)pc, S, (const void *)d_rounds);
+        auto it = c->v2_spent.find(key);
+        if (it == c->v2_spent.end()) {
+            if (c->v2_spent.size() > 64) {          // bounded: forget everything
+                for (auto &kv : c->v2_spent) cudaFree(kv.second);
+                c->v2_spent.clear();
+            }
+            int *p = nullptr;
+            CK(cudaMalloc(&p, sizeof(int) * 2 * (size_t)S));      // [rounds per source | SM per CTA]
+            CK(cudaMemsetAsync(p, 0, sizeof(int) * 2 * (size_t)S, c->stream));
+            it = c->v2_spent.emplace(key, p).first;
+        }
+        spent = it->second;
+    }
     int pk = phase_begin(c, PH_CONVERT);
     if (c->v2_pad_ptr != (void *)bufs || c->v2_pad_plan != pc || c->v2_pad_S < S || c->v2_pad_bytes != c->ws["fwd2_bufs"].second) {
         // every slot that is not a grid node must hold +inf; nothing ever writes those slots afterwards
@@ -447,7 +470,9 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     const int eb = elem_grid(c, d.N);
     k2_f_to_layouts<<<eb, 256, 0, c->stream>>>(P, df, flay, flay + P.M);
     LAUNCHED(c, "k2_f_to_layouts");
-    k2_u0_to_P<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, dU, bufs);
+    k2_make_order<<<1, 1024, 0, c->stream>>>(spent, spent + S, S, c->v2_pairing ? c->num_sms : 0, order);
+    LAUNCHED(c, "k2_make_order");
+    k2_u0_to_P<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, dU, bufs, order);
     LAUNCHED(c, "k2_u0_to_P");
     phase_end(c, pk);
     pk = phase_begin(c, PH_FWD);
@@ -460,7 +485,7 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
         if (occ < 1) occ = 1;                                                                                          \
         if (c->v2_occ > 0 && occ > c->v2_occ) occ = c->v2_occ;                                                         \
         kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol,    \
-                                                                                 max_rounds, S, d_rounds, d_errs, where); \
+                                                                                 max_rounds, S, d_rounds, d_errs, where, order, spent); \
     } while (0)
     if (P.NT <= 256) V2_LAUNCH(256, 2);
     else if (P.NT <= 320) V2_LAUNCH(320, 2);
@@ -471,7 +496,7 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     phase_end(c, pk);
     LAUNCHED(c, "k_fwd3d_v2");
     pk = phase_begin(c, PH_CONVERT);
-    k2_P_to_rowmajor<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, bufs, where, dU);
+    k2_P_to_rowmajor<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, bufs, where, dU, order);
     phase_end(c, pk);
     LAUNCHED(c, "k2_P_to_rowmajor");
     return 0;

@@ -382,7 +382,8 @@ __device__ __forceinline__ void v2_reskew(const Plan2 &P, const double *src, dou
 
 // bufs: S x 3 x M doubles; buffer 0 of every source holds u0 in layout P on entry, every slot that
 // is not a grid node holds +inf in all three buffers.  fP/fM: the slowness in layouts P and M.
-// where[src] receives the index (0..2) of the buffer holding the result (layout P).
+// where[slot] receives the index (0..2) of the buffer holding the result (layout P).
+// Buffer slot b holds source order[b] (see k2_make_order); rounds / errs are indexed by source.
 // One CTA per source at a time; sources are assigned statically (block-uniform control flow).
 // Dynamic shared memory: the re-skew plane, WCH x PS doubles.
 template <int NTMAX, int MINB>
@@ -390,7 +391,8 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v2(const Plan2 P, double 
                                                           const double *__restrict__ fP, const double *__restrict__ fM,
                                                           const double h, const double tol, const int max_rounds,
                                                           const int S, int *__restrict__ rounds, double *__restrict__ errs,
-                                                          int *__restrict__ where) {
+                                                          int *__restrict__ where, const int *__restrict__ order,
+                                                          int *__restrict__ spent) {
     extern __shared__ double plane[];
     __shared__ double red[32];
     for (int src = blockIdx.x; src < S; src += gridDim.x) {
@@ -418,13 +420,19 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v2(const Plan2 P, double 
 #undef V2_CALL
             }
             const double e = v2_block_max(err, red);
-            if (threadIdx.x == 0 && errs) errs[(long long)src * max_rounds + r] = e;
+            if (threadIdx.x == 0 && errs) errs[(long long)order[src] * max_rounds + r] = e;
             r++;
             const int oo = o; o = a; a = oo;      // the result (in a) becomes next round's round-start field
             if (__any_sync(0xffffffffu, e < tol)) { conv = true; break; }   // e is block-uniform; the vote makes that visible
         }
         if (threadIdx.x == 0) {
-            if (rounds) rounds[src] = conv ? r : -r;
+            if (rounds) rounds[order[src]] = conv ? r : -r;
+            spent[order[src]] = r;      // remembered: the next call with this batch pairs long sources with short ones
+            {
+                unsigned sm__;
+                asm("mov.u32 %0, %%smid;" : "=r"(sm__));
+                spent[S + src] = (int)sm__;   // ... using the SM this CTA ran on
+            }
             where[src] = o;
         }
         __syncthreads();
@@ -449,12 +457,71 @@ __global__ void k2_f_to_layouts(const Plan2 P, const double *__restrict__ f, dou
     }
 }
 
+// Which source goes into which buffer slot (= which CTA).  The number of rounds differs between sources
+// (4..7 on the bench batch) and two CTAs share an SM, so an SM that happens to get two long sources finishes
+// last.  The library remembers, per batch, the rounds every source needed in the previous call (spent[s];
+// 0: unknown) and on which SM every CTA of that call ran (smid[b]; the placement of a launch with the same
+// configuration repeats).  When both are known and all CTAs are resident at once (S <= 2 x SMs), the
+// sources that needed the most rounds go to the CTAs that have an SM to themselves and the others are
+// paired longest-with-shortest.  Anything else: caller order.  One CTA.
+__global__ void k2_make_order(const int *__restrict__ spent, const int *__restrict__ smid, const int S,
+                              const int nsm, int *__restrict__ order) {
+    __shared__ int known, n1;
+    if (threadIdx.x == 0) { known = 1; n1 = 0; }
+    __syncthreads();
+    for (int s = threadIdx.x; s < S; s += blockDim.x)
+        if (spent[s] <= 0 || smid[s] < 0) known = 0;
+    __syncthreads();
+    const bool paired = known && S > nsm && S <= 2 * nsm;
+    if (!paired) {
+        for (int s = threadIdx.x; s < S; s += blockDim.x) order[s] = s;
+        return;
+    }
+    // unit[b]: which rank CTA b takes.  Singles (in CTA order) take ranks 0..n1-1; pair number jp (pairs in the
+    // order of their lower CTA index) takes ranks n1+jp (lower CTA) and S-1-jp (upper CTA).
+    __shared__ int partner[1024], takes[1024];
+    if (S > 1024) {      // not reached: paired implies S <= 2 x SMs
+        for (int s = threadIdx.x; s < S; s += blockDim.x) order[s] = s;
+        return;
+    }
+    for (int b = threadIdx.x; b < S; b += blockDim.x) {
+        int same = 0, other = -1;
+        for (int t = 0; t < S; t++)
+            if (smid[t] == smid[b]) { same++; if (t != b) other = t; }
+        partner[b] = same == 2 ? other : -1;
+        if (same != 2) atomicAdd(&n1, 1);
+    }
+    __syncthreads();
+    const int nsingle = n1;
+    for (int b = threadIdx.x; b < S; b += blockDim.x) {
+        const int lowb = (partner[b] >= 0 && partner[b] < b) ? partner[b] : b;   // the unit's lower CTA
+        int js = 0, jp = 0;
+        for (int t = 0; t < lowb; t++) {
+            if (partner[t] < 0) js++;
+            else if (t < partner[t]) jp++;
+        }
+        takes[b] = partner[b] < 0 ? js : (b == lowb ? nsingle + jp : S - 1 - jp);
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        int rank = 0;                                  // descending by rounds, ties by index
+        const int ks = spent[s];
+        for (int t = 0; t < S; t++) {
+            const int kt = spent[t];
+            rank += (kt > ks || (kt == ks && t < s)) ? 1 : 0;
+        }
+        for (int b = 0; b < S; b++)
+            if (takes[b] == rank) order[b] = s;
+    }
+}
+
 // dense row-major u0 (S x N) -> buffer 0 of each source, layout P.  grid: (blocks, S)
-__global__ void k2_u0_to_P(const Plan2 P, const double *__restrict__ U0, double *__restrict__ bufs) {
+__global__ void k2_u0_to_P(const Plan2 P, const double *__restrict__ U0, double *__restrict__ bufs,
+                           const int *__restrict__ order) {
     const int n = P.ext[1], l = P.ext[2];
-    const int src = blockIdx.y;
-    const double *u0 = U0 + (long long)src * P.N;
-    double *b0 = bufs + (long long)src * 3 * P.M;
+    const int slot = blockIdx.y;
+    const double *u0 = U0 + (long long)order[slot] * P.N;
+    double *b0 = bufs + (long long)slot * 3 * P.M;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < P.N; id += gridDim.x * blockDim.x) {
         const int k = id % l, t = id / l, j = t % n, i = t / n;
         b0[v2_offset_ijk(P, i, j, k, +1)] = u0[id];
@@ -463,11 +530,11 @@ __global__ void k2_u0_to_P(const Plan2 P, const double *__restrict__ U0, double 
 
 // result (layout P, buffer where[src]) -> dense row-major U (S x N).  grid: (blocks, S)
 __global__ void k2_P_to_rowmajor(const Plan2 P, const double *__restrict__ bufs, const int *__restrict__ where,
-                                 double *__restrict__ U) {
+                                 double *__restrict__ U, const int *__restrict__ order) {
     const int n = P.ext[1], l = P.ext[2];
-    const int src = blockIdx.y;
-    const double *b = bufs + ((long long)src * 3 + where[src]) * P.M;
-    double *u = U + (long long)src * P.N;
+    const int slot = blockIdx.y;
+    const double *b = bufs + ((long long)slot * 3 + where[slot]) * P.M;
+    double *u = U + (long long)order[slot] * P.N;
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < P.N; id += gridDim.x * blockDim.x) {
         const int k = id % l, t = id / l, j = t % n, i = t / n;
         u[id] = b[v2_offset_ijk(P, i, j, k, +1)];
