@@ -426,8 +426,6 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
     // 16 warps: two CTAs per SM at 64 registers per thread
     const char *vw = getenv("ADTOMO_V2_WARPS");      // tuning aid
     pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
-    const char *vpf = getenv("ADTOMO_V2_PF");         // tuning aid
-    if (vpf) pc->plan.pf = atoi(vpf);
     pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
     c->plans2.push_back(pc);
     return pc;

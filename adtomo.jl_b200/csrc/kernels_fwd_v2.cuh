@@ -55,7 +55,6 @@ struct Plan2 {
     int G;               // column groups (of LC columns) per row
     int NT;              // threads per CTA
     int WCH, PS;         // re-skew: W rows per pass, plane pitch (even)
-    int pf;              // prefetch two levels ahead into L1 (tuning switch; no measurable effect once the loads are pipelined)
     long long M;         // slots per field buffer = (dA+2)*RS*PC
     long long N;
     int sg[8][3];        // (sA, sW, sC) of the reference's 8 sweeps (Eikonal3D.cpp:59-68) by role
@@ -135,29 +134,23 @@ EIK_HD void v2_load(const Plan2 &P, const V2Lane &L, const int lam, const int rb
     const int offA = SA * P.RS * P.PC, offW = SW * P.PC, offC = SW * P.PC + SC;   // downwind (old, level+1)
     const int offRB = V2_LA * (SA * P.RS - SW) * P.PC;
     const int wq = L.wqc + lam - rb * V2_LA - SC * g * V2_LC;
-    V.off = -1;
-    V.own = V.fv = V.dA = V.dW = V.dC = V.uA = V.uW = V.uC = V.ref = 0.0;
-    if ((unsigned)wq >= (unsigned)P.dW || rb * V2_LA + L.la >= P.dA || g * V2_LC + L.lc >= P.dC) return;
-    const int off = L.offc + rb * offRB + lam * offW + g * V2_LC;
-    V.off = off;
+    const bool act = (unsigned)wq < (unsigned)P.dW && rb * V2_LA + L.la < P.dA && g * V2_LC + L.lc < P.dC;
+    // a lane without a node loads from a harmless slot (A = 0, mu = 0: all six neighbour slots exist) instead of
+    // branching around the loads; it neither stores nor contributes to err
+    const int off = act ? L.offc + rb * offRB + lam * offW + g * V2_LC : (P.RS + 1) * P.PC + 1;
+    V.off = act ? off : -1;
     const double *p = rd + off;
     V.own = p[0];
     V.fv = fl[off];
     V.dA = p[offA];
     V.dW = p[offW];
     V.dC = p[offC];
-#if defined(__CUDA_ARCH__)
-    if (P.pf && (unsigned)(wq + 2) < (unsigned)P.dW) {   // the node this pencil reaches two levels ahead, its f one level ahead
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 2 * offW));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(fl + off + offW));
-    }
-#endif
     // upwind neighbours (new values of level-1, stored one barrier ago by this CTA); OOP: they live in wr
     const double *pu = OOP ? wr + off : p;
     V.uA = pu[-offA];
     V.uW = pu[-offW];
     V.uC = pu[-offC];
-    if (CMP) V.ref = cmp[off];
+    V.ref = CMP ? cmp[off] : 0.0;
 }
 
 // The update itself (Eikonal3D.cpp:47-54), in two steps so that the kernel can issue the next slot's
@@ -584,7 +577,6 @@ inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plan
     P.nlev = P.dA + P.dW + P.dC - 2;
     P.G = (P.dC + V2_LC - 1) / V2_LC;
     P.NT = 32 * nwarps;
-    P.pf = 0;
     P.PS = (P.dC + 1) & ~1;
     P.WCH = (int)(plane_bytes / (sizeof(double) * P.PS));
     if (P.WCH > P.dW) P.WCH = P.dW;
