@@ -60,6 +60,7 @@ struct adtomo_ctx {
     int force_v0 = 0;                           // debugging aid: ADTOMO_FORCE_V0=1 selects the row-major kernel
     int force_v1 = 0;                           // debugging aid: ADTOMO_FORCE_V1=1 selects the level-major kernel
     int force_v2 = 0;                           // debugging aid: ADTOMO_FORCE_V2=1 selects the skewed-pencil kernel for any batch
+    std::map<std::pair<long long, int>, int> chunk_cache;   // sources per chunk of the fused step, per (grid, batch)
     int v2_pairing = 1;                         // tuning aid: ADTOMO_V2_PAIRING=0 keeps sources in caller order
     std::map<std::tuple<const void *, int, const void *>, int *> v2_spent;   // rounds per source of earlier calls, per batch
     int v2_occ = 0;                             // tuning aid: ADTOMO_V2_OCC caps the CTAs per SM of the skewed-pencil kernel
@@ -432,8 +433,17 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
 }
 
 // Skewed-pencil path (kernels_fwd_v2.cuh): convert in, sweep, convert out.
+// u0 given as "fill value + sparse source lists" (what the inversion drivers build, inversion.jl:52-60) next to
+// its dense form: the skewed-pencil path initialises its own layout from the lists and never reads the dense field.
+struct SparseU0 {
+    const int *ptr, *idx;       // CSR over the sources of this call: entries ptr[s] .. ptr[s+1]-1 of idx / val
+    const double *val;
+    double fill;
+    const double *dense;        // S x N row-major, the same field
+};
+
 static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const double *df, const Dims3 &d, double h,
-                    double tol, int max_rounds, int S, int *d_rounds, double *d_errs) {
+                    double tol, int max_rounds, int S, int *d_rounds, double *d_errs, const SparseU0 *sp) {
     const Plan2 &P = pc->plan;
     double *bufs, *flay;
     int *where, *order, *spent;
@@ -470,8 +480,15 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     LAUNCHED(c, "k2_f_to_layouts");
     k2_make_order<<<1, 1024, 0, c->stream>>>(spent, spent + S, S, c->v2_pairing ? c->num_sms : 0, order);
     LAUNCHED(c, "k2_make_order");
-    k2_u0_to_P<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, dU, bufs, order);
-    LAUNCHED(c, "k2_u0_to_P");
+    if (sp) {
+        k2_fill_valid<<<dim3(32, S), 256, 0, c->stream>>>(P, bufs, sp->fill);
+        LAUNCHED(c, "k2_fill_valid");
+        k2_scatter_P<<<(S + 127) / 128, 128, 0, c->stream>>>(P, bufs, order, sp->ptr, sp->idx, sp->val, S);
+        LAUNCHED(c, "k2_scatter_P");
+    } else {
+        k2_u0_to_P<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, dU, bufs, order);
+        LAUNCHED(c, "k2_u0_to_P");
+    }
     phase_end(c, pk);
     pk = phase_begin(c, PH_FWD);
 #define V2_LAUNCH(NTMAX_, MINB_)                                                                                       \
@@ -502,7 +519,7 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
 
 // dU: S x N row-major, holds u0 on entry and the travel times on exit.
 static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3 &d, double h, double tol,
-                        int max_rounds, int S, int *d_rounds, double *d_errs) {
+                        int max_rounds, int S, int *d_rounds, double *d_errs, const SparseU0 *sp = nullptr) {
     PlanCache *pc = nullptr;
     int rc = get_plan(c, d.m, d.n, d.l, &pc);
     if (rc) return rc;
@@ -516,9 +533,11 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         const bool few = fits && (long long)S * cfg.CS <= c->num_sms;
         if (!few || c->force_v2) {
             const Plan2Cache *p2 = get_plan2(c, d.m, d.n, d.l);
-            if (p2->ok) return fwd3d_v2(c, p2, dU, df, d, h, tol, max_rounds, S, d_rounds, d_errs);
+            if (p2->ok) return fwd3d_v2(c, p2, dU, df, d, h, tol, max_rounds, S, d_rounds, d_errs, sp);
         }
     }
+    // the kernels below start from the dense field in dU
+    if (sp) CK(cudaMemcpyAsync(dU, sp->dense, sizeof(double) * (size_t)S * d.N, cudaMemcpyDeviceToDevice, c->stream));
     if (!c->force_v0 && fits) {
         // level-major path: convert in, sweep, convert out
         double *bufs, *flay, *errPart;
@@ -985,9 +1004,15 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     int Sc;
     {
         size_t per = (size_t)d.N * (13 * sizeof(double) + 8);
-        size_t budget = (size_t)(free_bytes() * 0.8);
-        for (auto &kv : c->ws) budget += kv.second.second;   // what we already hold is reusable
-        Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
+        const auto key = std::make_pair((long long)d.N, S);
+        auto it = c->chunk_cache.find(key);           // cudaMemGetInfo costs milliseconds: ask once per (grid, batch)
+        if (it != c->chunk_cache.end()) Sc = it->second;
+        else {
+            size_t budget = (size_t)(free_bytes() * 0.8);
+            for (auto &kv : c->ws) budget += kv.second.second;   // what we already hold is reusable
+            Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
+            c->chunk_cache[key] = Sc;
+        }
     }
     double *dU, *dU0, *dG = nullptr, *dMis, *dSum = nullptr, *dSumChunk = nullptr;
     int *dR, *dSt;
@@ -1016,8 +1041,8 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
         LAUNCHED(c, "k_fill");
         k_scatter_sources<<<(sc + 127) / 128, 128, 0, c->stream>>>(dU0, dptr + s0, didx, dval, d.N, sc);
         LAUNCHED(c, "k_scatter_sources");
-        CK(cudaMemcpyAsync(dU, dU0, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, c->stream));
-        if ((rc = fwd3d_device(c, dU, df, d, h, tol, max_rounds, sc, dR + s0, nullptr))) return rc;
+        const SparseU0 sp = {dptr + s0, didx, dval, u0_fill, dU0};
+        if ((rc = fwd3d_device(c, dU, df, d, h, tol, max_rounds, sc, dR + s0, nullptr, &sp))) return rc;
         if (grad_f) CK(cudaMemsetAsync(dG, 0, sizeof(double) * cnt, c->stream));
         dim3 g((E + 127) / 128, sc);
         int pkm = phase_begin(c, PH_MISFIT);

@@ -508,6 +508,37 @@ __global__ void k2_make_order(const int *__restrict__ spent, const int *__restri
     }
 }
 
+// u0 = `value` at every grid node of buffer 0 of each slot, written row by row of layout P (coalesced).
+// grid: (blocks, S), 256 threads.  Used with k2_scatter_P when the sources are given as sparse lists.
+__global__ void k2_fill_valid(const Plan2 P, double *__restrict__ bufs, const double value) {
+    double *b0 = bufs + (long long)blockIdx.y * 3 * P.M;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nrows = P.dA * P.nmu;
+    for (int row = blockIdx.x * nw + warp; row < nrows; row += gridDim.x * nw) {
+        const int A = row / P.nmu, mu = row - A * P.nmu;
+        const int c0 = mu - P.dW + 1 > 0 ? mu - P.dW + 1 : 0, c1 = mu < P.dC - 1 ? mu : P.dC - 1;
+        double *r = b0 + ((long long)(A + 1) * P.RS + (mu + 1)) * P.PC;
+        for (int C = c0 + lane; C <= c1; C += 32) r[C] = value;
+    }
+}
+
+// sparse source values into buffer 0 of each slot (layout P); slot b holds source order[b].  One thread per
+// slot, entries in list order (later entries win, like the Julia assignments of inversion.jl:52-60).
+__global__ void k2_scatter_P(const Plan2 P, double *__restrict__ bufs, const int *__restrict__ order,
+                             const int *__restrict__ src_ptr, const int *__restrict__ src_idx,
+                             const double *__restrict__ src_val, const int S) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= S) return;
+    const int s = order[slot];
+    const int n = P.ext[1], l = P.ext[2];
+    double *b0 = bufs + (long long)slot * 3 * P.M;
+    for (int q = src_ptr[s]; q < src_ptr[s + 1]; q++) {
+        const int id = src_idx[q];
+        const int k = id % l, t = id / l, j = t % n, i = t / n;
+        b0[v2_offset_ijk(P, i, j, k, +1)] = src_val[q];
+    }
+}
+
 // dense row-major u0 (S x N) -> buffer 0 of each source, layout P.  grid: (blocks, S)
 __global__ void k2_u0_to_P(const Plan2 P, const double *__restrict__ U0, double *__restrict__ bufs,
                            const int *__restrict__ order) {
