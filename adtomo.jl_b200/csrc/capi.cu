@@ -1076,6 +1076,11 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     CK(cudaMemcpyAsync(hs.data(), dSt, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (misfit) *misfit = hm;
+    if (getenv("ADTOMO_DEBUG_WAVES")) {      // debugging aid: depth of the adjoint's dependency graph
+        long long tot = 0; int mx = 0;
+        for (int s = 0; s < S; s++) { tot += abs(hs[s]); mx = std::max(mx, abs(hs[s])); }
+        fprintf(stderr, "[adtomo] adjoint wavefront: mean waves %.1f max %d\n", (double)tot / S, mx);
+    }
     int st = rounds_status(hr, rounds);
     if (grad_f)
         for (int s = 0; s < S; s++)
