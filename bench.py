@@ -300,7 +300,7 @@ def run_ours(args):
     achieved = kern[dom]["gbs"]
     # DRAM bytes of that kernel from the committed ncu --set full capture of this same launch (profiles/)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_v2.json")   # k_fwd3d_v2<512,2>, the kernel this batch runs on
     if dom == "forward_sweeps" and S == S_PER_GPU and (m, n, l) == GRID and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_gb_per_launch")
     step_alg_gbs = (bf + ba) / 1e6 / (ms_dev / args.steps)
