@@ -615,14 +615,17 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
         // and the per-wave barrier cost falls with the number of threads that share it.)  ADTOMO_ADJ_NT: tuning aid.
         static const int adj_nt_env = getenv("ADTOMO_ADJ_NT") ? atoi(getenv("ADTOMO_ADJ_NT")) : 0;
         const int adj_nt = adj_nt_env ? adj_nt_env : 1024;
+        static const int adj_agg_env = getenv("ADTOMO_ADJ_AGG") ? atoi(getenv("ADTOMO_ADJ_AGG")) : -1;
+        const bool adj_agg = adj_agg_env >= 0 ? adj_agg_env != 0 : true;
         pk = phase_begin(c, PH_ADJ_SWEEP);
 #define ADJ_LAUNCH(NT_)                                                                                               \
     do {                                                                                                              \
         int occ = 1;                                                                                                  \
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo2<NT_>, NT_, 0));                          \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo2<NT_, true>, NT_, 0));                    \
         if (occ < 1) occ = 1;                                                                                         \
         const int grid = std::min(S, c->num_sms * occ);                                                               \
-        k_adj3d_topo2<NT_><<<grid, NT_, 0, c->stream>>>(UX, GD, CM, (unsigned int *)cnt, Q, cnts + S, cnts, d, S, d_status); \
+        if (adj_agg) k_adj3d_topo2<NT_, true><<<grid, NT_, 0, c->stream>>>(UX, GD, CM, (unsigned int *)cnt, Q, cnts + S, cnts, d, S, d_status); \
+        else k_adj3d_topo2<NT_, false><<<grid, NT_, 0, c->stream>>>(UX, GD, CM, (unsigned int *)cnt, Q, cnts + S, cnts, d, S, d_status); \
     } while (0)
         if (adj_nt <= 256) ADJ_LAUNCH(256);
         else if (adj_nt <= 512) ADJ_LAUNCH(512);

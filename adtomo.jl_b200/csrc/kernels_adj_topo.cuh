@@ -97,7 +97,7 @@ __global__ void k_adj3d_count2(const unsigned char *__restrict__ code, unsigned 
     }
 }
 
-template <int NT>
+template <int NT, bool AGG>
 __global__ void __launch_bounds__(NT) k_adj3d_topo2(double2 *UX, const double2 *__restrict__ GD,
                                                     const unsigned short *__restrict__ CM, unsigned int *cnt32,
                                                     int *Q, const int *__restrict__ qtail,
@@ -149,7 +149,10 @@ __global__ void __launch_bounds__(NT) k_adj3d_topo2(double2 *UX, const double2 *
         const long long gq = base + (p);                                         \
         const unsigned sh = (unsigned)(gq & 3) * 8u;                             \
         const unsigned old = atomicSub(&cnt32[gq >> 2], 1u << sh);               \
-        if (((old >> sh) & 0xFFu) == 1u) rp = (int)(p);                          \
+        if (((old >> sh) & 0xFFu) == 1u) {                                       \
+            if (AGG) rp = (int)(p);                                              \
+            else q[atomicAdd(&s_tail, 1)] = (int)(p);                            \
+        }                                                                        \
     }
                     TOPO_RELEASE(ci, ci == 1 ? id - nl : id + nl, rp0)
                     TOPO_RELEASE(cj, cj == 1 ? id - l : id + l, rp1)
@@ -168,9 +171,11 @@ __global__ void __launch_bounds__(NT) k_adj3d_topo2(double2 *UX, const double2 *
             if (rp >= 0) q[pos + __popc(m & lt)] = rp;                                     \
         }                                                                                  \
     }
-                TOPO_PUSH(rp0)
-                TOPO_PUSH(rp1)
-                TOPO_PUSH(rp2)
+                if (AGG) {
+                    TOPO_PUSH(rp0)
+                    TOPO_PUSH(rp1)
+                    TOPO_PUSH(rp2)
+                }
 #undef TOPO_PUSH
             }
             __syncthreads();

@@ -35,14 +35,18 @@ def main():
     res = {}
 
     def timeit(fn, reps=3, warm=1):
+        """Median wall time of `reps` synchronised calls (single-source cases are milliseconds long and the first
+        calls after an allocation are 2x slower, so a mean of 3 was noise)."""
         for _ in range(warm):
             fn()
         ctx.synchronize()
-        t0 = time.perf_counter()
+        ts = []
         for _ in range(reps):
+            t0 = time.perf_counter()
             fn()
-        ctx.synchronize()
-        return 1e3 * (time.perf_counter() - t0) / reps
+            ctx.synchronize()
+            ts.append(1e3 * (time.perf_counter() - t0))
+        return float(np.median(ts))
 
     # ---- C1
     if "c1" not in args.skip:
@@ -62,7 +66,7 @@ def main():
         ms = timeit(c1, reps=20, warm=3)
         res["C1_2d_30x40_S40_host_buffers"] = {"ms": ms, "solves_per_s": S / ms * 1e3, "rounds_mean": float(rounds.mean())}
 
-    def single_source(name, u0, f, h, tol, reps=3):
+    def single_source(name, u0, f, h, tol, reps=9):
         m, n, l = u0.shape
         N = u0.size
         d_u0 = torch.from_numpy(u0.reshape(1, -1).copy()).to(dev)
@@ -73,8 +77,8 @@ def main():
         rounds = np.zeros(1, dtype=np.int32)
         fw = lambda: ctx.forward3d_batch(d_u, d_u0, d_f, h, (m, n, l), tol, 1, rounds=rounds, loc=A.DEVICE)
         bw = lambda: ctx.backward3d_batch(None, None, d_gs, d_g, d_u, d_u0, d_f, h, (m, n, l), 1, loc=A.DEVICE)
-        ms_f = timeit(fw, reps=reps)
-        ms_b = timeit(bw, reps=reps)
+        ms_f = timeit(fw, reps=reps, warm=2)
+        ms_b = timeit(bw, reps=reps, warm=2)
         K = int(rounds[0])
         alg = 8.0 * N * (8 + 48 * K)
         res[name] = {"forward_ms": ms_f, "adjoint_ms": ms_b, "solves_per_s": 1e3 / (ms_f + ms_b), "rounds": K,
@@ -97,7 +101,7 @@ def main():
         vel = syn.gil7_velocity(m, n, l, hh)
         u0 = np.full((m, n, l), 1000.0)
         u0[m // 2, n // 2, 0] = 0.0
-        single_source("C5_256cubed_GIL7", u0, 1.0 / vel, hh, 1e-6, reps=1)
+        single_source("C5_256cubed_GIL7", u0, 1.0 / vel, hh, 1e-6, reps=3)
 
     # ---- C4: one rank's shard of the joint inversion
     if "c4" not in args.skip:
