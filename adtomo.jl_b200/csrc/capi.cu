@@ -17,6 +17,7 @@
 #include "kernels_adj_topo.cuh"
 #include "kernels_fwd_v1.cuh"
 #include "kernels_fwd_v2.cuh"
+#include "kernels_fwd_team.cuh"
 #include "nccl_dyn.h"
 
 using namespace adtomo;
@@ -70,6 +71,20 @@ struct adtomo_ctx {
     size_t v2_pad_bytes = 0;
     const struct Plan2Cache *v2_pad_plan = nullptr;
     int v2_pad_S = 0;
+    // team kernel (kernels_fwd_team.cuh): few sources, many CTAs per source
+    int team_mode = -1;                         // ADTOMO_TEAM: -1 automatic, 0 never, 1 whenever a team shape exists
+    int team_rows = 0;                          // tuning aid: ADTOMO_TEAM_R forces the rows per CTA
+    std::vector<struct Plan2Cache *> plans_team;
+    void *team_pad_ptr = nullptr;
+    size_t team_pad_bytes = 0;
+    const struct Plan2Cache *team_pad_plan = nullptr;
+    int team_pad_S = 0;
+    // mailbox tags only grow (kernels_fwd_team.cuh): next free sweep serial; the mailbox is cleared when the
+    // buffer changes or the 20-bit serial space is used up
+    unsigned team_serial = 0;
+    void *team_mbox_ptr = nullptr;
+    size_t team_mbox_bytes = 0;
+    int team_nt = 512;                          // tuning aid: ADTOMO_TEAM_NT = 512 (two CTAs per SM) | 1024 (one)
 };
 
 struct Plan2Cache {
@@ -171,6 +186,12 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     c->fwd_variant = fvv ? atoi(fvv) : 0;
     const char *fcl = getenv("ADTOMO_FORCE_CLUSTER");
     c->force_cluster = fcl ? atoi(fcl) : 0;
+    const char *tm = getenv("ADTOMO_TEAM");
+    c->team_mode = tm ? atoi(tm) : -1;
+    const char *tmr = getenv("ADTOMO_TEAM_R");
+    c->team_rows = tmr ? atoi(tmr) : 0;
+    const char *tnt = getenv("ADTOMO_TEAM_NT");
+    c->team_nt = (tnt && atoi(tnt) == 1024) ? 1024 : 512;
     *out = c;
     return 0;
 }
@@ -187,6 +208,7 @@ extern "C" int adtomo_destroy(adtomo_ctx *c) {
     }
     if (c->nccl_comm) adtomo_nccl_finalize(c);
     for (auto *pc : c->plans2) delete pc;
+    for (auto *pc : c->plans_team) delete pc;
     for (auto &kv : c->v2_spent) cudaFree(kv.second);
     for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaEventDestroy(c->ev0);
@@ -517,6 +539,97 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Team path (kernels_fwd_team.cuh): few sources, every source on a team of co-resident CTAs.
+// ---------------------------------------------------------------------------------------------
+static Plan2Cache *get_plan_team(adtomo_ctx *c, int m, int n, int l) {
+    for (auto *pc : c->plans_team)
+        if (pc->m == m && pc->n == n && pc->l == l) return pc;
+    Plan2Cache *pc = new Plan2Cache();
+    pc->m = m; pc->n = n; pc->l = l;
+    pc->ok = team_build_plan(pc->plan, m, n, l, c->team_nt / 32, 64 * 1024);
+    pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
+    c->plans_team.push_back(pc);
+    return pc;
+}
+
+static const void *team_kernel(adtomo_ctx *c) {
+    return c->team_nt == 1024 ? (const void *)k_fwd3d_team<1024, 1> : (const void *)k_fwd3d_team<512, 2>;
+}
+
+// CTAs of k_fwd3d_team the device holds at once (cooperative launch limit)
+static int team_max_ctas(adtomo_ctx *c, const Plan2Cache *pc) {
+    const void *kern = team_kernel(c);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c->team_nt, pc->smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return occ * c->num_sms;
+}
+
+static int fwd3d_team(adtomo_ctx *c, const Plan2Cache *pc, const TeamCfg &T, double *dU, const double *df, const Dims3 &d,
+                      double h, double tol, int max_rounds, int S, int *d_rounds, double *d_errs, const SparseU0 *sp) {
+    const Plan2 &P = pc->plan;
+    double *bufs, *flay;
+    int *where, *order;
+    unsigned *sync;
+    tm_u64 *mbox;
+    const size_t nb = (size_t)S * 3 * P.M;
+    const size_t mbn = (size_t)S * T.nC * 2 * (size_t)T.mbStride;
+    WS(c, "team_bufs", double, nb, bufs);
+    WS(c, "team_flay", double, (size_t)2 * P.M, flay);
+    WS(c, "team_where", int, 2 * (size_t)S, where);
+    WS(c, "team_sync", unsigned, (size_t)S * TM_SYNC_WORDS, sync);
+    WS(c, "team_mbox", tm_u64, mbn, mbox);
+    order = where + S;
+    int pk = phase_begin(c, PH_CONVERT);
+    if (c->team_pad_ptr != (void *)bufs || c->team_pad_plan != pc || c->team_pad_S < S || c->team_pad_bytes != c->ws["team_bufs"].second) {
+        k2_fill<<<c->num_sms * 8, 512, 0, c->stream>>>(bufs, (long long)nb, v2_inf());
+        LAUNCHED(c, "k2_fill");
+        c->team_pad_ptr = bufs; c->team_pad_plan = pc; c->team_pad_S = S; c->team_pad_bytes = c->ws["team_bufs"].second;
+    }
+    // serial range of this launch: 8 sweeps per round; no packet in the mailbox may carry a tag of this range
+    const unsigned need = 8u * (unsigned)max_rounds + 1u;
+    const unsigned serial_max = (1u << (32 - TM_LEVEL_BITS)) - 1u;
+    if (need >= serial_max) return fail(ADTOMO_ERR_ARG, "max_rounds %d too large for the team kernel", max_rounds);
+    if (c->team_mbox_ptr != (void *)mbox || c->team_mbox_bytes != c->ws["team_mbox"].second || c->team_serial + need >= serial_max) {
+        CK(cudaMemsetAsync(mbox, 0, c->ws["team_mbox"].second, c->stream));
+        c->team_mbox_ptr = mbox; c->team_mbox_bytes = c->ws["team_mbox"].second; c->team_serial = 0;
+    }
+    unsigned serial0 = c->team_serial;
+    c->team_serial += need;
+    CK(cudaMemsetAsync(sync, 0, sizeof(unsigned) * (size_t)S * TM_SYNC_WORDS, c->stream));
+    const int eb = elem_grid(c, d.N);
+    k2_f_to_layouts<<<eb, 256, 0, c->stream>>>(P, df, flay, flay + P.M);
+    LAUNCHED(c, "k2_f_to_layouts");
+    k2_identity<<<(S + 127) / 128, 128, 0, c->stream>>>(order, S);
+    LAUNCHED(c, "k2_identity");
+    if (sp) {
+        k2_fill_valid<<<dim3(32, S), 256, 0, c->stream>>>(P, bufs, sp->fill);
+        LAUNCHED(c, "k2_fill_valid");
+        k2_scatter_P<<<(S + 127) / 128, 128, 0, c->stream>>>(P, bufs, order, sp->ptr, sp->idx, sp->val, S);
+        LAUNCHED(c, "k2_scatter_P");
+    } else {
+        k2_u0_to_P<<<dim3(std::max(1, std::min(eb, 4 * c->num_sms / S)), S), 256, 0, c->stream>>>(P, dU, bufs, order);
+        LAUNCHED(c, "k2_u0_to_P");
+    }
+    phase_end(c, pk);
+    pk = phase_begin(c, PH_FWD);
+    {
+        Plan2 Pv = P;
+        TeamCfg Tv = T;
+        const double *fPp = flay, *fMp = flay + P.M;
+        void *args[] = {&Pv, &Tv, &bufs, &fPp, &fMp, &h, &tol, &max_rounds, &d_rounds, &d_errs, &where, &sync, &mbox, &serial0};
+        CK(cudaLaunchCooperativeKernel(team_kernel(c), dim3(S * T.nC), dim3(c->team_nt), args, pc->smem_bytes, c->stream));
+    }
+    phase_end(c, pk);
+    LAUNCHED(c, "k_fwd3d_team");
+    pk = phase_begin(c, PH_CONVERT);
+    k2_P_to_rowmajor<<<dim3(std::max(1, std::min(eb, 4 * c->num_sms / S)), S), 256, 0, c->stream>>>(P, bufs, where, dU, order);
+    phase_end(c, pk);
+    LAUNCHED(c, "k2_P_to_rowmajor");
+    return 0;
+}
+
 // dU: S x N row-major, holds u0 on entry and the travel times on exit.
 static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3 &d, double h, double tol,
                         int max_rounds, int S, int *d_rounds, double *d_errs, const SparseU0 *sp = nullptr) {
@@ -529,6 +642,16 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
     // Kernel choice.  Few sources (every source gets its own SM or cluster of SMs in ONE wave): the
     // level-major kernel, which puts 1024 threads (x cluster size) on a source.  A batch that oversubscribes
     // the SMs: the skewed-pencil kernel (two sources per SM, no shared-memory limit on the grid size).
+    // Few sources: a team of CTAs per source (every source gets >= 8 CTAs, or ADTOMO_TEAM=1).
+    if (!c->force_v0 && !c->force_v1 && !c->force_v2 && !c->force_cluster && c->team_mode != 0) {
+        const Plan2Cache *pt = get_plan_team(c, d.m, d.n, d.l);
+        TeamCfg T;
+        if (pt->ok) {
+            const int maxc = team_max_ctas(c, pt);
+            if (maxc > 0 && team_config(pt->plan, S, maxc, c->team_nt / 32, c->team_rows, T) && (T.nC >= 8 || c->team_mode == 1))
+                return fwd3d_team(c, pt, T, dU, df, d, h, tol, max_rounds, S, d_rounds, d_errs, sp);
+        }
+    }
     if (!c->force_v0 && !c->force_v1 && !c->force_cluster) {
         const bool few = fits && (long long)S * cfg.CS <= c->num_sms;
         if (!few || c->force_v2) {

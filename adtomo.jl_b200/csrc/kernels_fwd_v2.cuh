@@ -358,9 +358,10 @@ __device__ __forceinline__ void v2_reskew_pass(const Plan2 &P, const double *s, 
     }
 }
 
+// slabs A in [A0, A1): the team kernel (kernels_fwd_team.cuh) gives every CTA of a team its own slabs
 __device__ __forceinline__ void v2_reskew(const Plan2 &P, const double *src, double *dst, const int sigmaFrom,
-                                          double *plane) {
-    for (int A = 0; A < P.dA; A++) {
+                                          double *plane, const int A0, const int A1) {
+    for (int A = A0; A < A1; A++) {
         const double *s = src + (long long)(A + 1) * P.RS * P.PC;
         double *d = dst + (long long)(A + 1) * P.RS * P.PC;
         for (int w0 = 0; w0 < P.dW; w0 += P.WCH) {
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v2(const Plan2 P, double 
                 if (sw > 0 && sigma != state) {
                     double *dst = state > 0 ? Bz : Ba;
                     __syncthreads();
-                    v2_reskew(P, w, dst, state, plane);
+                    v2_reskew(P, w, dst, state, plane, 0, P.dA);
                     w = dst;
                     state = sigma;
                 }
@@ -574,7 +575,9 @@ __global__ void k2_P_to_rowmajor(const Plan2 P, const double *__restrict__ bufs,
 // and dA of 4, a warp slot is live for dW + 10 levels of which dW are fully used, and role assignments
 // with A = k need 6 instead of 4 layout changes per round.  nwarps: warps per CTA.
 // Returns false when the grid cannot be handled (more than 32 column groups, 32-bit slots).
-inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plane_bytes) {
+// LA x LC: the lane patch the plan is scored for (the team kernel uses 1 x 32 and has no limit on the groups).
+inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plane_bytes, int LA = V2_LA,
+                          int LC = V2_LC, int maxG = 32) {
     static const int SG[8][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, -1, 1}, {1, -1, 1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, -1}};
     const int ext[3] = {m, n, l};
     double best = -1.0;
@@ -582,8 +585,8 @@ inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plan
     static const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
     for (int p = 0; p < 6; p++) {
         const int dA = ext[perms[p][0]], dW = ext[perms[p][1]], dC = ext[perms[p][2]];
-        const int G = (dC + V2_LC - 1) / V2_LC;
-        if (G > 32) continue;      // lane g of a warp computes the window of column group g
+        const int G = (dC + LC - 1) / LC;
+        if (G > maxG) continue;    // v2: lane g of a warp computes the window of column group g
         // layout changes per round (sigma = sW*sC along the reference's sweep order, cyclic)
         int changes = 0;
         for (int s = 0; s < 8; s++) {
@@ -591,10 +594,10 @@ inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plan
             const int s1 = SG[(s + 1) % 8][perms[p][1]] * SG[(s + 1) % 8][perms[p][2]];
             changes += (s0 != s1);
         }
-        const double fill = (double)dC / (V2_LC * G);
-        const double live = (double)dW / (dW + V2_LC + V2_LA - 2);
-        const int nrb = (dA + V2_LA - 1) / V2_LA;
-        const double afill = (double)dA / (nrb * V2_LA);
+        const double fill = (double)dC / (LC * G);
+        const double live = (double)dW / (dW + LC + LA - 2);
+        const int nrb = (dA + LA - 1) / LA;
+        const double afill = (double)dA / (nrb * LA);
         double score = fill * live * afill * (1.0 - 0.02 * changes);
         if (perms[p][2] == 2) score *= 1.01;      // tie-break: lanes along the grid's fastest axis
         if (score > best) { best = score; for (int q = 0; q < 3; q++) bestRole[q] = perms[p][q]; }
@@ -606,7 +609,7 @@ inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plan
     P.RS = P.nmu + 2;
     P.PC = ((P.dC + 1 + 3) / 4) * 4;
     P.nlev = P.dA + P.dW + P.dC - 2;
-    P.G = (P.dC + V2_LC - 1) / V2_LC;
+    P.G = (P.dC + LC - 1) / LC;
     P.NT = 32 * nwarps;
     P.PS = (P.dC + 1) & ~1;
     P.WCH = (int)(plane_bytes / (sizeof(double) * P.PS));

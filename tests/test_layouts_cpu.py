@@ -113,3 +113,64 @@ def test_v2_plan_roles(emul2):
     assert list(out)[:3] == [0, 1, 2] and out[5] == 512         # A = i, W = j, C = k
     assert emul2.emul_v2_plan(200, 200, 80, 16, PLANE, out) == 1 and out[2] == 2   # no shared-memory limit any more
     assert emul2.emul_v2_plan(512, 512, 512, 16, PLANE, out) == 0                  # 64 column groups > 32 lanes
+
+
+# ----------------------------------------------------------------------------------------------
+# team kernel (kernels_fwd_team.cuh): rows of one source split over many CTAs that synchronise through
+# progress words only; the emulation advances the CTAs in random / extreme orders allowed by that rule
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emul_team():
+    so = os.path.join(HERE, "emul", "libemul_team.so")
+    src = os.path.join(HERE, "emul", "emulate_team.cpp")
+    deps = [src] + [os.path.join(HERE, "..", "adtomo.jl_b200", "csrc", n)
+                    for n in ("kernels_fwd_team.cuh", "kernels_fwd_v2.cuh", "eik_core.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
+    L = ctypes.CDLL(so)
+    L.emul_team_forward.restype = ctypes.c_int
+    L.emul_team_forward.argtypes = [_dp, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_uint, _dp]
+    L.emul_team_config.restype = ctypes.c_int
+    L.emul_team_config.argtypes = [ctypes.c_int] * 7 + [ctypes.POINTER(ctypes.c_int)]
+    return L
+
+
+@pytest.mark.parametrize("dims,tol,max_ctas,rforce,policy", [
+    ((2, 2, 2), 1e-9, 296, 0, 0), ((5, 4, 3), 1e-9, 296, 0, 0), ((3, 9, 4), 1e-6, 2, 0, 0), ((9, 7, 6), 1e-6, 296, 0, 1),
+    ((12, 12, 12), 1e-3, 296, 0, 2), ((7, 3, 11), 0.0, 3, 0, 0), ((16, 12, 6), 1e-6, 296, 2, 0),
+    ((6, 16, 12), 1e-6, 5, 0, 1), ((12, 6, 16), 1e-4, 296, 0, 2), ((24, 19, 15), 1e-3, 7, 0, 0),
+    ((33, 9, 10), 1e-6, 296, 3, 0), ((10, 35, 9), 1e-6, 296, 0, 1), ((9, 10, 41), 1e-6, 4, 0, 2),
+    ((21, 21, 21), 1e-9, 296, 0, 0), ((9, 8, 70), 1e-6, 296, 0, 0), ((40, 5, 33), 1e-6, 296, 0, 2),
+    ((20, 40, 9), 1e-6, 1, 0, 0)])
+def test_emulated_team_bitexact(emul_team, oracle, dims, tol, max_ctas, rforce, policy):
+    rng = np.random.default_rng(sum(dims) + 11)
+    f = 0.5 + rng.random(dims)
+    u0 = np.full(dims, 1000.0)
+    for _ in range(2):
+        u0[tuple(rng.integers(0, d) for d in dims)] = float(rng.random() * 0.1)
+    h = 0.3
+    u_ref, r_ref, e_ref = oracle.eikonal3d_forward(u0, f, h, tol)
+    u = u0.copy()
+    errs = np.zeros(20)
+    r = emul_team.emul_team_forward(u.ctypes.data_as(_dp), f.ctypes.data_as(_dp), *dims, h, tol, 20, 16, PLANE,
+                                    max_ctas, rforce, policy, 12345, errs.ctypes.data_as(_dp))
+    assert r > -1000, "no plan fits / pads were overwritten / a dead slot held a node / scheduler deadlock"
+    assert abs(r) == r_ref and (r > 0) == (tol > 0)
+    assert errs[abs(r) - 1] == e_ref
+    np.testing.assert_array_equal(u, u_ref)
+
+
+def test_team_config(emul_team):
+    out = (ctypes.c_int * 6)()
+    # one 256^3 source on 2 x 148 CTAs: 2 rows per CTA give every one of the 16 warps a slot (8 groups of 32)
+    assert emul_team.emul_team_config(256, 256, 256, 1, 296, 16, 0, out) == 1
+    assert list(out)[3:] == [128, 2, 8]
+    assert emul_team.emul_team_config(512, 512, 512, 1, 296, 16, 0, out) == 1
+    assert list(out)[3:] == [256, 2, 16]
+    # 16 sources share the device: 18 CTAs each
+    assert emul_team.emul_team_config(128, 128, 64, 16, 296, 16, 0, out) == 1
+    assert out[3] <= 18 and out[3] * out[4] >= 128
+    # more sources than CTAs: no team
+    assert emul_team.emul_team_config(64, 64, 64, 400, 296, 16, 0, out) == 0
