@@ -18,6 +18,7 @@
 #include "kernels_fwd_v1.cuh"
 #include "kernels_fwd_v2.cuh"
 #include "kernels_fwd_team.cuh"
+#include "kernels_adj_team.cuh"
 #include "nccl_dyn.h"
 
 using namespace adtomo;
@@ -84,7 +85,8 @@ struct adtomo_ctx {
     unsigned team_serial = 0;
     void *team_mbox_ptr = nullptr;
     size_t team_mbox_bytes = 0;
-    int team_nt = 512;                          // tuning aid: ADTOMO_TEAM_NT = 512 (two CTAs per SM) | 1024 (one)
+    int team_nt = 512;                          // 16 warps, <= 64 registers: two CTAs per SM
+    int adj_team = 0;                           // tuning aid: ADTOMO_ADJ_TEAM = CTAs per source of the adjoint wavefront (0: automatic, 1: single-CTA kernel)
 };
 
 struct Plan2Cache {
@@ -188,10 +190,10 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     c->force_cluster = fcl ? atoi(fcl) : 0;
     const char *tm = getenv("ADTOMO_TEAM");
     c->team_mode = tm ? atoi(tm) : -1;
+    const char *atm = getenv("ADTOMO_ADJ_TEAM");
+    c->adj_team = atm ? atoi(atm) : 0;
     const char *tmr = getenv("ADTOMO_TEAM_R");
     c->team_rows = tmr ? atoi(tmr) : 0;
-    const char *tnt = getenv("ADTOMO_TEAM_NT");
-    c->team_nt = (tnt && atoi(tnt) == 1024) ? 1024 : 512;
     *out = c;
     return 0;
 }
@@ -553,16 +555,18 @@ static Plan2Cache *get_plan_team(adtomo_ctx *c, int m, int n, int l) {
     return pc;
 }
 
-static const void *team_kernel(adtomo_ctx *c) {
-    return c->team_nt == 1024 ? (const void *)k_fwd3d_team<1024, 1> : (const void *)k_fwd3d_team<512, 2>;
+static const void *team_kernel(int) { return (const void *)k_fwd3d_team<512, 2>; }
+static size_t team_smem(const Plan2Cache *pc, const TeamCfg &T) {
+    return std::max(pc->smem_bytes, sizeof(double) * 2 * (size_t)T.R * T.SP);
 }
+static int team_ks(const TeamCfg &T, int nt) { return T.R * T.G32 <= nt / 32 ? 1 : 2; }
 
 // CTAs of k_fwd3d_team the device holds at once (cooperative launch limit)
-static int team_max_ctas(adtomo_ctx *c, const Plan2Cache *pc) {
-    const void *kern = team_kernel(c);
+static int team_max_ctas(adtomo_ctx *c, int KS, size_t smem) {
+    const void *kern = team_kernel(KS);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) { cudaGetLastError(); return 0; }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c->team_nt, pc->smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c->team_nt, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     return occ * c->num_sms;
 }
 
@@ -619,7 +623,8 @@ static int fwd3d_team(adtomo_ctx *c, const Plan2Cache *pc, const TeamCfg &T, dou
         TeamCfg Tv = T;
         const double *fPp = flay, *fMp = flay + P.M;
         void *args[] = {&Pv, &Tv, &bufs, &fPp, &fMp, &h, &tol, &max_rounds, &d_rounds, &d_errs, &where, &sync, &mbox, &serial0};
-        CK(cudaLaunchCooperativeKernel(team_kernel(c), dim3(S * T.nC), dim3(c->team_nt), args, pc->smem_bytes, c->stream));
+        CK(cudaLaunchCooperativeKernel(team_kernel(team_ks(T, c->team_nt)), dim3(S * T.nC), dim3(c->team_nt), args,
+                                       team_smem(pc, T), c->stream));
     }
     phase_end(c, pk);
     LAUNCHED(c, "k_fwd3d_team");
@@ -647,8 +652,11 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
         const Plan2Cache *pt = get_plan_team(c, d.m, d.n, d.l);
         TeamCfg T;
         if (pt->ok) {
-            const int maxc = team_max_ctas(c, pt);
-            if (maxc > 0 && team_config(pt->plan, S, maxc, c->team_nt / 32, c->team_rows, T) && (T.nC >= 8 || c->team_mode == 1))
+            // the CTA budget depends on the kernel variant and the shared memory, which depend on the team shape:
+            // shape from the budget of the common case, then re-check the shape's own budget
+            const int maxc = team_max_ctas(c, 2, pt->smem_bytes);
+            if (maxc > 0 && team_config(pt->plan, S, maxc, c->team_nt / 32, c->team_rows, T) && (T.nC >= 8 || c->team_mode == 1) &&
+                team_smem(pt, T) <= 100 * 1024 && S * T.nC <= team_max_ctas(c, team_ks(T, c->team_nt), team_smem(pt, T)))
                 return fwd3d_team(c, pt, T, dU, df, d, h, tol, max_rounds, S, d_rounds, d_errs, sp);
         }
     }
@@ -723,8 +731,8 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
     WS(c, "adj_cm", unsigned short, total, CM);
     WS(c, "adj_cnt", unsigned char, (total + 7) & ~(size_t)3, cnt);
     WS(c, "adj_queue", int, total, Q);
-    WS(c, "adj_counters", int, 3 * (size_t)S, cnts);
-    CK(cudaMemsetAsync(cnts, 0, sizeof(int) * 3 * S, c->stream));
+    WS(c, "adj_counters", int, 8 * (size_t)S, cnts);     // [0,S) free nodes, [S,2S) queue tails, [2S,3S) barrier counters, [4S,8S) push counters
+    CK(cudaMemsetAsync(cnts, 0, sizeof(int) * 8 * S, c->stream));
     const dim3 eg(std::min(elem_grid(c, d.N), 128), S);
     int pk = phase_begin(c, PH_ADJ_SETUP);
     k_adj3d_setup2<<<eg, 256, 0, c->stream>>>(dU, dU0, dG, UX, GD, dGU0, code, cnts, d, S);
@@ -741,6 +749,31 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
         static const int adj_agg_env = getenv("ADTOMO_ADJ_AGG") ? atoi(getenv("ADTOMO_ADJ_AGG")) : -1;
         const bool adj_agg = adj_agg_env >= 0 ? adj_agg_env != 0 : true;
         pk = phase_begin(c, PH_ADJ_SWEEP);
+        // Few sources: a team of CTAs per source works on every wave (kernels_adj_team.cuh).
+        {
+            constexpr int ANT = 512;
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo_team<ANT>, ANT, 0) != cudaSuccess) { cudaGetLastError(); occ = 0; }
+            const int budget = occ * c->num_sms / S;
+            int nC = c->adj_team > 0 ? std::min(c->adj_team, budget) : std::min(budget, 64);
+            if (c->team_mode == 0 && c->adj_team == 0) nC = 1;
+            if (nC >= 8 || (c->adj_team > 1 && nC > 1)) {
+                const int *tail0 = cnts + S, *nfree = cnts;
+                int *Dp = cnts + 4 * S;
+                unsigned *bar = (unsigned *)(cnts + 2 * S);
+                unsigned int *cnt32 = (unsigned int *)cnt;
+                Dims3 dd = d;
+                void *args[] = {&UX, &GD, &CM, &cnt32, &Q, &tail0, &Dp, &nfree, &dd, &nC, &bar, &d_status};
+                CK(cudaLaunchCooperativeKernel((const void *)k_adj3d_topo_team<ANT>, dim3(S * nC), dim3(ANT), args, 0, c->stream));
+                phase_end(c, pk);
+                LAUNCHED(c, "k_adj3d_topo_team");
+                pk = phase_begin(c, PH_ADJ_FINISH);
+                k_adj3d_finish2<<<elem_grid(c, d.N), 256, 0, c->stream>>>(UX, df, dGF, dGFsum, d.N, S, h);
+                phase_end(c, pk);
+                LAUNCHED(c, "k_adj3d_finish2");
+                return 0;
+            }
+        }
 #define ADJ_LAUNCH(NT_)                                                                                               \
     do {                                                                                                              \
         int occ = 1;                                                                                                  \

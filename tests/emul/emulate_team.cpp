@@ -1,6 +1,6 @@
 // tests/emul/emulate_team.cpp -- TEST INFRASTRUCTURE.  A serial host emulation of the team kernel
-// (adtomo.jl_b200/csrc/kernels_fwd_team.cuh): it runs the kernel's OWN per-lane functions (tm_slot = tm_load +
-// tm_finish, tm_rows, tm_slot_live, v2_reskew_elem; compiled for the host) with the same plan, team shape,
+// (adtomo.jl_b200/csrc/kernels_fwd_team.cuh): it runs the kernel's OWN per-lane functions (tm_load_old, tm_prep,
+// tm_solve, tm_rows, tm_slot_live, v2_reskew_elem; compiled for the host) with the same plan, team shape,
 // buffers, mailbox and round loop.  The CTAs of the team are advanced slot by slot by a scheduler (random, or
 // "upstream as far ahead as possible", or "downstream as close as possible") that only honours what the kernel
 // itself waits for: the CTA's level barrier, and the arrival of the tagged mailbox packets of a first-row slot.
@@ -18,12 +18,20 @@ using namespace adtomo;
 
 // One sweep: the CTAs advance slot by slot.  A CTA works on one level at a time (its __syncthreads); inside the
 // level its pending slots run in any order; a slot of the CTA's first row is runnable only when the packets of
-// all its nodes have arrived (right tag) -- exactly what the kernel's spin waits for.
+// all its nodes have arrived (right tag) -- exactly what the kernel's spin waits for.  Every CTA has its two
+// sheets.  The kernel may read a node's OLD values as early as one level ahead (L1 prefetch): the emulation
+// reads them when the slot's PREVIOUS level runs and keeps them until they are used.
 template <int SA, int SW, int SC, bool OOP, bool CMP>
 static void sweep_t(const Plan2 &P, const TeamCfg &T, const double *rd, double *wr, const double *fl, const double *cmp,
                     double h, double &err, std::mt19937 &rng, int policy, std::vector<tm_u64> &mbox, unsigned base) {
     const int nC = T.nC;
-    struct Cta { int a0, a1, lam, lam1; std::vector<int> pending; };
+    struct Cta {
+        int a0, a1, lam, lam1;
+        std::vector<int> pending;
+        std::vector<double> sheets;
+        std::vector<TmOld> early;      // [slot][lane]: old values read one level ahead
+        std::vector<char> has_early;   // [slot]
+    };
     std::vector<Cta> cta(nC);
     auto fill = [&](Cta &c) {
         c.pending.clear();
@@ -36,7 +44,11 @@ static void sweep_t(const Plan2 &P, const TeamCfg &T, const double *rd, double *
                     if (Wp >= 0 && Wp < P.dW && Cp < P.dC) has = true;
                 }
                 if (tm_slot_live(P, c.lam, Ap, g)) c.pending.push_back(q);
-                else if (has) err = NAN;              // a slot declared dead must not contain a node
+                else {
+                    if (has) err = NAN;               // a slot declared dead must not contain a node
+                    for (int lane = 0; lane < 32; lane++)   // the kernel's dead-slot branch
+                        c.sheets[((c.lam & 1) * T.R + r) * T.SP + g * TM_LC + lane + 1] = INFINITY;
+                }
             }
             if (c.pending.empty()) c.lam++;
         }
@@ -45,21 +57,22 @@ static void sweep_t(const Plan2 &P, const TeamCfg &T, const double *rd, double *
         int l0;
         tm_rows(P, T, t, cta[t].a0, cta[t].a1, l0, cta[t].lam1);
         cta[t].lam = l0;
+        cta[t].sheets.assign((size_t)2 * T.R * T.SP, INFINITY);
+        cta[t].early.resize((size_t)(cta[t].a1 - cta[t].a0) * T.G32 * 32);
+        cta[t].has_early.assign((size_t)(cta[t].a1 - cta[t].a0) * T.G32, 0);
         fill(cta[t]);
     }
     auto runnable = [&](int t, int q) {
         const Cta &c = cta[t];
         const int r = q / T.G32, g = q - r * T.G32, Ap = c.a0 + r;
-        if (t == 0 || Ap != c.a0) return true;
+        if (t == 0 || r != 0) return true;
         const tm_u64 *inbox = mbox.data() + (long long)t * 2 * T.mbStride;
         for (int lane = 0; lane < 32; lane++) {
-            const int Cp = g * TM_LC + lane, Wp = c.lam - Ap - Cp;
-            if (!(Wp >= 0 && Wp < P.dW && Cp < P.dC)) continue;
-            const int C = SC > 0 ? Cp : P.dC - 1 - Cp;
-            const int mu = SW > 0 ? c.lam - Ap : P.nmu - 1 - (c.lam - Ap);
-            const long long mb = (long long)(mu + 1) * P.PC + C;
+            int off, mb;
+            tm_addr<SA, SW, SC>(P, lane, c.lam, Ap, g, off, mb);
+            if (off < 0) continue;
             double v;
-            if (!tm_unpack(inbox[2 * mb], inbox[2 * mb + 1], base | (unsigned)c.lam, v)) return false;
+            if (!tm_unpack(inbox[2 * (long long)mb], inbox[2 * (long long)mb + 1], base | (unsigned)c.lam, v)) return false;
         }
         return true;
     };
@@ -78,12 +91,26 @@ static void sweep_t(const Plan2 &P, const TeamCfg &T, const double *rd, double *
         if (policy == 0) pick = ready[rng() % ready.size()];
         else if (policy == 1) pick = ready.front();     // low ranks run as far ahead as they can
         else pick = ready.back();                       // high ranks follow as closely as they can
-        Cta &c = cta[pick.first];
+        const int t = pick.first;
+        Cta &c = cta[t];
         const int q = c.pending[pick.second];
         c.pending.erase(c.pending.begin() + pick.second);
-        const int r = q / T.G32, g = q - r * T.G32, Ap = c.a0 + r;
+        const int r = q / T.G32, g = q - r * T.G32, Ap = c.a0 + r, nrow = c.a1 - c.a0;
+        TmPrep Q[32];
+        for (int lane = 0; lane < 32; lane++) {
+            TmOld O;
+            if (c.has_early[q]) O = c.early[(size_t)q * 32 + lane];
+            else tm_load_old<SA, SW, SC, CMP>(P, lane, c.lam, Ap, g, rd, fl, cmp, O);
+            tm_prep<SA, SW, SC>(P, T, t, lane, c.lam, r, Ap, g, O, mbox.data(), base, c.sheets.data(), Q[lane]);
+        }
+        c.has_early[q] = 0;
+        if (tm_slot_live(P, c.lam + 1, Ap, g)) {        // the prefetch: next level's old values are read NOW
+            for (int lane = 0; lane < 32; lane++)
+                tm_load_old<SA, SW, SC, CMP>(P, lane, c.lam + 1, Ap, g, rd, fl, cmp, c.early[(size_t)q * 32 + lane]);
+            c.has_early[q] = 1;
+        }
         for (int lane = 0; lane < 32; lane++)
-            tm_slot<SA, SW, SC, OOP, CMP>(P, T, pick.first, c.a0, c.a1, lane, c.lam, Ap, g, rd, wr, fl, cmp, h, err, mbox.data(), base);
+            tm_solve<OOP, CMP>(T, t, nrow, lane, c.lam, r, g, Q[lane], wr, h, err, mbox.data(), base, c.sheets.data());
         if (c.pending.empty()) { c.lam++; fill(c); }
     }
 }

@@ -164,9 +164,9 @@ def test_emulated_team_bitexact(emul_team, oracle, dims, tol, max_ctas, rforce, 
 
 def test_team_config(emul_team):
     out = (ctypes.c_int * 6)()
-    # one 256^3 source on 2 x 148 CTAs: 2 rows per CTA give every one of the 16 warps a slot (8 groups of 32)
+    # one 256^3 source on 2 x 148 CTAs: one row per CTA (8 groups of 32 columns)
     assert emul_team.emul_team_config(256, 256, 256, 1, 296, 16, 0, out) == 1
-    assert list(out)[3:] == [128, 2, 8]
+    assert list(out)[3:] == [256, 1, 8]
     assert emul_team.emul_team_config(512, 512, 512, 1, 296, 16, 0, out) == 1
     assert list(out)[3:] == [256, 2, 16]
     # 16 sources share the device: 18 CTAs each
