@@ -555,7 +555,10 @@ static Plan2Cache *get_plan_team(adtomo_ctx *c, int m, int n, int l) {
     return pc;
 }
 
-static const void *team_kernel(int) { return (const void *)k_fwd3d_team<512, 2>; }
+// KS: slots per warp whose per-sweep constants stay in registers
+static const void *team_kernel(int KS) {
+    return KS <= 1 ? (const void *)k_fwd3d_team<512, 2, 1> : (const void *)k_fwd3d_team<512, 2, 2>;
+}
 static size_t team_smem(const Plan2Cache *pc, const TeamCfg &T) {
     return std::max(pc->smem_bytes, sizeof(double) * 2 * (size_t)T.R * T.SP);
 }

@@ -98,20 +98,54 @@ inline void tm_mb_store(tm_u64 *slot, const tm_u64 p0, const tm_u64 p1) { slot[0
 inline void tm_mb_load(const tm_u64 *slot, tm_u64 &p0, tm_u64 &p1) { p0 = slot[0]; p1 = slot[1]; }
 #endif
 
-// Slot of one lane's node of warp slot (row Ap, column group g) at level lam; coordinates with a prime are
-// counted in the sweep's direction.  Same offsets as v2_load, computed per slot.  off: slot in the field buffers
-// (< 0: the lane has no node at this level), mb: slot inside its slab = mailbox slot.
+// rows [a0, a1) of team member t, first and last level at which one of them has a node
+EIK_HD void tm_rows(const Plan2 &P, const TeamCfg &T, const int t, int &a0, int &a1, int &lam0, int &lam1) {
+    a0 = t * T.R;
+    a1 = a0 + T.R < P.dA ? a0 + T.R : P.dA;
+    lam0 = a0;
+    lam1 = a1 - 1 + P.dW - 1 + P.dC - 1;
+}
+
+// Per-lane constants of one warp slot (row r of the CTA = row Ap of the sweep, column group g) for a whole
+// sweep; coordinates with a prime are counted in the sweep's direction.  The lane's node at level lam is
+// (Ap, W' = lam - wsum, C' = Cp); its slot in the field buffers is offc + lam * (SW * PC) -- affine in the level
+// (same layout arithmetic as v2_load) -- and its slot inside its slab (= mailbox slot) is that minus slab.
+struct TmSlotC {
+    int wsum;    // Ap + Cp
+    int offc;    // field slot at level 0
+    int slab;    // (A + 1) * RS * PC
+    int sidx;    // sheet index r * SP + Cp + 1
+    int flags;
+};
+enum { TM_COL = 1, TM_FIRST = 2, TM_LAST = 4, TM_RPOS = 8 };   // column exists; uA from the mailbox; packet to send; uA from the sheet
+
 template <int SA, int SW, int SC>
-EIK_HD void tm_addr(const Plan2 &P, const int lane, const int lam, const int Ap, const int g, int &off, int &mb) {
-    const int Cp = g * TM_LC + lane;
-    const int Wp = lam - Ap - Cp;
-    const bool act = (unsigned)Wp < (unsigned)P.dW && Cp < P.dC;
+EIK_HD void tm_slot_setup(const Plan2 &P, const TeamCfg &T, const int t, const int a0, const int nrow, const int lane,
+                          const int q, TmSlotC &K) {
+    const int r = q / T.G32, g = q - r * T.G32;
+    const int Ap = a0 + r, Cp = g * TM_LC + lane;
     const int A = SA > 0 ? Ap : P.dA - 1 - Ap;
     const int C = SC > 0 ? Cp : P.dC - 1 - Cp;
-    const int mu = SW > 0 ? lam - Ap : P.nmu - 1 - (lam - Ap);      // uniform over the warp: one skewed row
-    mb = (mu + 1) * P.PC + C;
-    off = act ? (A + 1) * P.RS * P.PC + mb : -1;
+    K.wsum = Ap + Cp;
+    K.slab = (A + 1) * P.RS * P.PC;
+    // mu + 1 = lam - Ap + 1 (SW > 0) or nmu - lam + Ap (SW < 0): one skewed row per level, uniform over the warp
+    K.offc = K.slab + (SW > 0 ? 1 - Ap : P.nmu + Ap) * P.PC + C;
+    K.sidx = r * T.SP + Cp + 1;
+    K.flags = (Cp < P.dC ? TM_COL : 0) | ((t > 0 && r == 0) ? TM_FIRST : 0) |
+              ((t < T.nC - 1 && r == nrow - 1) ? TM_LAST : 0) | (r > 0 ? TM_RPOS : 0);
 }
+
+// does the lane have a node at level lam?
+EIK_HD bool tm_act(const Plan2 &P, const TmSlotC &K, const int lam) {
+    return (unsigned)(lam - K.wsum) < (unsigned)P.dW && (K.flags & TM_COL);
+}
+// warp-uniform: does the slot have a node at level lam?  (lane j has W' = top - j)
+EIK_HD bool tm_slot_live(const Plan2 &P, const TmSlotC &K, const int lane, const int lam) {
+    const int top = lam - (K.wsum - lane);
+    return top >= 0 && top - (TM_LC - 1) < P.dW;
+}
+template <int SW>
+EIK_HD int tm_off(const Plan2 &P, const TmSlotC &K, const int lam) { return K.offc + lam * (SW * P.PC); }
 
 // OLD values of the node: nothing in the sweep writes them before level lam (own) / lam + 1 (downwind).
 struct TmOld {
@@ -120,13 +154,11 @@ struct TmOld {
 };
 
 template <int SA, int SW, int SC, bool CMP>
-EIK_HD void tm_load_old(const Plan2 &P, const int lane, const int lam, const int Ap, const int g, const double *rd,
+EIK_HD void tm_load_old(const Plan2 &P, const TmSlotC &K, const int lam, const double *rd,
                         const double *__restrict__ fl, const double *cmp, TmOld &O) {
     const int offA = SA * P.RS * P.PC, offW = SW * P.PC, offC = SW * P.PC + SC;   // downwind (old, level+1)
-    int off, mb;
-    tm_addr<SA, SW, SC>(P, lane, lam, Ap, g, off, mb);
     // a lane without a node loads from a harmless slot (A = 0, mu = 0: all neighbour slots exist)
-    if (off < 0) off = (P.RS + 1) * P.PC + 1;
+    const int off = tm_act(P, K, lam) ? tm_off<SW>(P, K, lam) : (P.RS + 1) * P.PC + 1;
     const double *p = rd + off;
     O.own = TM_LDU(p);
     O.fv = fl[off];
@@ -136,68 +168,64 @@ EIK_HD void tm_load_old(const Plan2 &P, const int lane, const int lam, const int
     O.ref = CMP ? TM_LDU(cmp + off) : 0.0;
 }
 
-// L1 prefetch of what tm_load_old will read at level lam (one 32-byte sector per 4 lanes; the lanes of a
-// slot read contiguous runs, so a few lanes would do, but predicating them costs as much as issuing all).
+// L1 prefetch of what tm_load_old will read TM_PF levels ahead and no earlier level touches: the row of level
+// lam + TM_PF + 1 of this slab (dW, dC), the A-neighbour's row, slowness, round-start value.  One level ahead
+// covers an L2 hit; the fields of a 256^3 source (3 x 215 MB + mailboxes) do not fit L2 and a DRAM miss takes
+// longer than a level (measured level time 0.68 / 0.83 / 1.17 us at 64^3 / 128^3 / 256^3 with TM_PF = 1).
+#ifndef TM_PF
+#define TM_PF 3
+#endif
 template <int SA, int SW, int SC, bool CMP>
-EIK_HD void tm_prefetch_old(const Plan2 &P, const int lane, const int lam, const int Ap, const int g, const double *rd,
+EIK_HD void tm_prefetch_old(const Plan2 &P, const TmSlotC &K, const int lam, const double *rd,
                             const double *__restrict__ fl, const double *cmp) {
+    if (!tm_act(P, K, lam + TM_PF)) return;
     const int offA = SA * P.RS * P.PC, offW = SW * P.PC;
-    int off, mb;
-    tm_addr<SA, SW, SC>(P, lane, lam, Ap, g, off, mb);
-    if (off < 0) return;
-    TM_PREFETCH(rd + off + offW);      // row of level lam+1 in this slab: dW, dC (own was dW one level ago)
+    const int off = tm_off<SW>(P, K, lam + TM_PF);
+    TM_PREFETCH(rd + off + offW);
     TM_PREFETCH(rd + off + offA);
     TM_PREFETCH(fl + off);
     if (CMP) TM_PREFETCH(cmp + off);
 }
 
-// NEW (level lam-1) values of the node of lane column Cp in the CTA's row r: from the sheet of level lam-1
-// (pitch SP, column Cp at index Cp+1, index 0 = +inf), the A neighbour of the CTA's first row from the mailbox
-// (inbox != nullptr; packets tagged tag_in) or +inf (the grid's first row).
+// One warp slot at level lam, for one lane, in two steps (loads + ordering, then arithmetic + stores).
+// base = sweep serial << TM_LEVEL_BITS; a packet of level L carries tag base | (L + 1).
+// sheets: [2][R][SP] doubles, sheet (lam & 1) receives this level, the other one holds level lam-1:
+// column Cp at index Cp+1, index 0 = +inf.  The A neighbour of the CTA's first row comes from the mailbox
+// (inbox = mbox + t * 2 * mbStride, packets tagged base | lam) or is +inf (the grid's first row).
 // Host build: a packet that has not arrived yields NaN (the emulation's scheduler must prevent that).
-EIK_HD void tm_load_new(const double *sheetPrev, const int SP, const int r, const int Cp, const bool act,
-                        const tm_u64 *inbox, const int mb, const unsigned tag_in, double &uA, double &uW, double &uC) {
-    const double *row = sheetPrev + r * SP + Cp;
-    uC = row[0];
-    uW = row[1];
-    if (r > 0) {
-        uA = row[1 - SP];
-    } else if (inbox) {
+struct TmPrep {
+    double a1, a2, a3, own, fv, ref;
+    int off;      // field slot, < 0: no node
+};
+
+template <int SA, int SW, int SC>
+EIK_HD void tm_prep(const Plan2 &P, const TeamCfg &T, const TmSlotC &K, const int lam, const TmOld &O,
+                    const tm_u64 *inbox, const unsigned base, const double *sheets, TmPrep &Q) {
+    const bool act = tm_act(P, K, lam);
+    const int off = tm_off<SW>(P, K, lam);
+    Q.off = act ? off : -1;
+    const double *row = sheets + ((lam & 1) ^ 1) * T.R * T.SP + K.sidx;
+    const double uC = row[-1], uW = row[0];
+    double uA;
+    if (K.flags & TM_RPOS) {
+        uA = row[-T.SP];
+    } else if (K.flags & TM_FIRST) {
         uA = 0.0;
         if (act) {
             // the A-neighbour has the same (W, C), i.e. the same slot inside ITS slab
+            const tm_u64 *pk = inbox + 2 * (long long)(off - K.slab);
+            const unsigned tag = base | (unsigned)lam;
             tm_u64 p0, p1;
 #if defined(__CUDA_ARCH__)
-            do { tm_mb_load(inbox + 2 * (long long)mb, p0, p1); } while (!tm_unpack(p0, p1, tag_in, uA));
+            do { tm_mb_load(pk, p0, p1); } while (!tm_unpack(p0, p1, tag, uA));
 #else
-            tm_mb_load(inbox + 2 * (long long)mb, p0, p1);
-            if (!tm_unpack(p0, p1, tag_in, uA)) uA = NAN;
+            tm_mb_load(pk, p0, p1);
+            if (!tm_unpack(p0, p1, tag, uA)) uA = NAN;
 #endif
         }
     } else {
         uA = v2_inf();
     }
-}
-
-// One warp slot (row r of the CTA = row Ap of the sweep, column group g) at level lam, for one lane, in two
-// steps so that the kernel can issue the next level's loads in between (their registers are free once tm_prep
-// has consumed O).  base = sweep serial << TM_LEVEL_BITS; a packet of level L carries tag base | (L + 1).
-// sheets: [2][R][SP] doubles, sheet (lam & 1) receives this level.
-struct TmPrep {
-    double a1, a2, a3, own, fv, ref;
-    int off, mb;
-};
-
-template <int SA, int SW, int SC>
-EIK_HD void tm_prep(const Plan2 &P, const TeamCfg &T, const int t, const int lane, const int lam, const int r,
-                    const int Ap, const int g, const TmOld &O, const tm_u64 *mbox, const unsigned base,
-                    const double *sheets, TmPrep &Q) {
-    tm_addr<SA, SW, SC>(P, lane, lam, Ap, g, Q.off, Q.mb);
-    // mbox: the team's inboxes, inbox of member t at mbox + t * 2 * mbStride
-    const tm_u64 *inbox = (t > 0 && r == 0) ? mbox + (long long)t * 2 * T.mbStride : nullptr;
-    const double *prev = sheets + ((lam & 1) ^ 1) * T.R * T.SP;
-    double uA, uW, uC;
-    tm_load_new(prev, T.SP, r, g * TM_LC + lane, Q.off >= 0, inbox, Q.mb, base | (unsigned)lam, uA, uW, uC);
     Q.own = O.own;
     Q.fv = O.fv;
     Q.ref = O.ref;
@@ -208,12 +236,11 @@ EIK_HD void tm_prep(const Plan2 &P, const TeamCfg &T, const int t, const int lan
 }
 
 // The update (Eikonal3D.cpp:47-54), its store, its sheet entry (+inf when the lane has no node) and the packet
-// for the downstream CTA (the node is in the CTA's last row; written for EVERY node of the row, changed or not:
-// the consumer waits for it).
+// for the downstream CTA (outbox = mbox + (t + 1) * 2 * mbStride; written for EVERY node of the CTA's last row,
+// changed or not: the consumer waits for it).
 template <bool OOP, bool CMP>
-EIK_HD void tm_solve(const TeamCfg &T, const int t, const int nrow, const int lane, const int lam, const int r,
-                     const int g, const TmPrep &Q, double *wr, const double h, double &err, tm_u64 *mbox,
-                     const unsigned base, double *sheets) {
+EIK_HD void tm_solve(const TeamCfg &T, const TmSlotC &K, const int lam, const TmPrep &Q, double *wr, const double h,
+                     double &err, tm_u64 *outbox, const unsigned base, double *sheets) {
     double res = v2_inf();
     if (Q.off >= 0) {
         res = Q.own;
@@ -223,32 +250,17 @@ EIK_HD void tm_solve(const TeamCfg &T, const int t, const int nrow, const int la
             if (un < Q.own) { res = un; changed = true; }
         }
         if (OOP || changed) wr[Q.off] = res;
-        if (t < T.nC - 1 && r == nrow - 1) {
-            tm_u64 *outbox = mbox + (long long)(t + 1) * 2 * T.mbStride;
+        if (K.flags & TM_LAST) {
             tm_u64 p0, p1;
             tm_pack(res, base | (unsigned)(lam + 1), p0, p1);
-            tm_mb_store(outbox + 2 * (long long)Q.mb, p0, p1);
+            tm_mb_store(outbox + 2 * (long long)(Q.off - K.slab), p0, p1);
         }
         if (CMP) {
             const double dd = fabs(res - Q.ref);
             err = (err < dd) ? dd : err;
         }
     }
-    sheets[((lam & 1) * T.R + r) * T.SP + g * TM_LC + lane + 1] = res;
-}
-
-// rows [a0, a1) of team member t, first and last level at which one of them has a node
-EIK_HD void tm_rows(const Plan2 &P, const TeamCfg &T, const int t, int &a0, int &a1, int &lam0, int &lam1) {
-    a0 = t * T.R;
-    a1 = a0 + T.R < P.dA ? a0 + T.R : P.dA;
-    lam0 = a0;
-    lam1 = a1 - 1 + P.dW - 1 + P.dC - 1;
-}
-
-// warp-uniform: does slot (Ap, g) have a node at level lam?
-EIK_HD bool tm_slot_live(const Plan2 &P, const int lam, const int Ap, const int g) {
-    const int top = lam - Ap - g * TM_LC;          // W' of lane 0; lane j has W' = top - j
-    return top >= 0 && top - (TM_LC - 1) < P.dW;
+    sheets[(lam & 1) * T.R * T.SP + K.sidx] = res;
 }
 
 #if defined(__CUDACC__)
@@ -273,8 +285,9 @@ __device__ __forceinline__ void tm_barrier(unsigned *ctr, unsigned &epoch, const
     __syncthreads();
 }
 
-// One sweep of team member t.  A warp owns slots q = warp, warp + nw, ... for the whole sweep.
-template <int SA, int SW, int SC, bool OOP, bool CMP>
+// One sweep of team member t.  A warp owns slots q = warp, warp + nw, ... for the whole sweep; the constants of
+// its first KS slots stay in registers, further slots (grids wider than KS x 512 columns per row) recompute them.
+template <int SA, int SW, int SC, bool OOP, bool CMP, int KS>
 __device__ __forceinline__ void tm_sweep(const Plan2 &P, const TeamCfg &T, const int t, const double *rd, double *wr,
                                          const double *__restrict__ fl, const double *cmp, const double h,
                                          double &err, tm_u64 *mbox, const unsigned base, double *sheets) {
@@ -282,25 +295,39 @@ __device__ __forceinline__ void tm_sweep(const Plan2 &P, const TeamCfg &T, const
     int a0, a1, lam0, lam1;
     tm_rows(P, T, t, a0, a1, lam0, lam1);
     const int nrow = a1 - a0, nslot = nrow * T.G32;
+    const tm_u64 *inbox = mbox + (long long)t * 2 * T.mbStride;
+    tm_u64 *outbox = mbox + (long long)(t + 1) * 2 * T.mbStride;
     for (int i = threadIdx.x; i < 2 * T.R * T.SP; i += blockDim.x) sheets[i] = v2_inf();
+    TmSlotC K[KS];
+#pragma unroll
+    for (int k = 0; k < KS; k++)
+        if (warp + k * nw < nslot) tm_slot_setup<SA, SW, SC>(P, T, t, a0, nrow, lane, warp + k * nw, K[k]);
     __syncthreads();
+#define TM_STEP(K_)                                                                                   \
+    do {                                                                                              \
+        if (!tm_slot_live(P, K_, lane, lam)) {      /* no node: the sheet still needs its +inf */    \
+            sheets[(lam & 1) * T.R * T.SP + (K_).sidx] = v2_inf();                                    \
+        } else {                                                                                      \
+            TmOld O;                                                                                  \
+            TmPrep Q;                                                                                 \
+            tm_prefetch_old<SA, SW, SC, CMP>(P, K_, lam, rd, fl, cmp);                                \
+            tm_load_old<SA, SW, SC, CMP>(P, K_, lam, rd, fl, cmp, O);                                 \
+            tm_prep<SA, SW, SC>(P, T, K_, lam, O, inbox, base, sheets, Q);                            \
+            tm_solve<OOP, CMP>(T, K_, lam, Q, wr, h, err, outbox, base, sheets);                      \
+        }                                                                                             \
+    } while (0)
     for (int lam = lam0; lam <= lam1; lam++) {
-        for (int q = warp; q < nslot; q += nw) {
-            const int r = q / T.G32, g = q - r * T.G32;
-            if (tm_slot_live(P, lam + 1, a0 + r, g))      // warp-uniform; beyond lam1 no slot is live
-                tm_prefetch_old<SA, SW, SC, CMP>(P, lane, lam + 1, a0 + r, g, rd, fl, cmp);
-            if (!tm_slot_live(P, lam, a0 + r, g)) {       // no node: the sheet still needs its +inf
-                sheets[((lam & 1) * T.R + r) * T.SP + g * TM_LC + lane + 1] = v2_inf();
-                continue;
-            }
-            TmOld O;
-            TmPrep Q;
-            tm_load_old<SA, SW, SC, CMP>(P, lane, lam, a0 + r, g, rd, fl, cmp, O);
-            tm_prep<SA, SW, SC>(P, T, t, lane, lam, r, a0 + r, g, O, mbox, base, sheets, Q);
-            tm_solve<OOP, CMP>(T, t, nrow, lane, lam, r, g, Q, wr, h, err, mbox, base, sheets);
+#pragma unroll
+        for (int k = 0; k < KS; k++)
+            if (warp + k * nw < nslot) TM_STEP(K[k]);
+        for (int q = warp + KS * nw; q < nslot; q += nw) {
+            TmSlotC G;
+            tm_slot_setup<SA, SW, SC>(P, T, t, a0, nrow, lane, q, G);
+            TM_STEP(G);
         }
         __syncthreads();
     }
+#undef TM_STEP
 }
 
 // bufs: S x 3 x M doubles as in k_fwd3d_v2 (buffer 0 of every source: u0 in layout P; every slot that is
@@ -308,7 +335,7 @@ __device__ __forceinline__ void tm_sweep(const Plan2 &P, const TeamCfg &T, const
 // sync: S x TM_SYNC_WORDS unsigned words, zero on entry.  mbox: S x nC inboxes of mbStride packets; no tag in
 // it is >= (serial0 + 1) << TM_LEVEL_BITS (the host hands out serial ranges and clears the mailbox on wrap).
 // Dynamic shared memory: max(re-skew plane, two sheets of R x SP doubles); they are never live together.
-template <int NTMAX, int MINB>
+template <int NTMAX, int MINB, int KS>
 __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_team(const Plan2 P, const TeamCfg T, double *bufs,
                                                             const double *__restrict__ fP, const double *__restrict__ fM,
                                                             const double h, const double tol, const int max_rounds,
@@ -346,7 +373,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_team(const Plan2 P, const
             serial++;
             const unsigned base = serial << TM_LEVEL_BITS;
 #define TM_CALL(a_, w_, c_, oop_, cmp_) \
-    tm_sweep<a_, w_, c_, oop_, cmp_>(P, T, t, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err, mbox, base, plane)
+    tm_sweep<a_, w_, c_, oop_, cmp_, KS>(P, T, t, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err, mbox, base, plane)
             V2_DISPATCH(P, sw, TM_CALL);
 #undef TM_CALL
         }

@@ -6,7 +6,7 @@
 C1: 2D 30x40 model, 40 sources, forward + adjoint           (tests/2D_test.jl shape)
 C2: 3D 64^3 layered, 1 source and tests/test3d.jl 51^3       (latency-bound single source)
 C4: 3D 200x200x80, S sources on this GPU (one rank's shard of the 2048), fused misfit + gradient
-C5: 3D 256^3 single source forward + adjoint
+C5: 3D 256^3 / 384^3 / 512^3 single source forward + adjoint (team kernels: the whole GPU on one source)
 Each entry: milliseconds (CUDA events of the library's stream), source-solves/s, rounds, and the
 algorithmic GB/s of SURVEY 8(d).  Inputs are device resident (loc=DEVICE) unless noted."""
 import argparse
@@ -96,12 +96,15 @@ def main():
 
     # ---- C5
     if "c5" not in args.skip:
-        m = n = l = 256
-        hh = 25.0 / l
-        vel = syn.gil7_velocity(m, n, l, hh)
-        u0 = np.full((m, n, l), 1000.0)
-        u0[m // 2, n // 2, 0] = 0.0
-        single_source("C5_256cubed_GIL7", u0, 1.0 / vel, hh, 1e-6, reps=3)
+        for sz in (256, 384, 512):
+            m = n = l = sz
+            hh = 25.0 / l
+            vel = syn.gil7_velocity(m, n, l, hh)
+            u0 = np.full((m, n, l), 1000.0)
+            u0[m // 2, n // 2, 0] = 0.0
+            single_source(f"C5_{sz}cubed_GIL7", u0, 1.0 / vel, hh, 1e-6, reps=3)
+            del vel, u0
+            torch.cuda.empty_cache()
 
     # ---- C4: one rank's shard of the joint inversion
     if "c4" not in args.skip:

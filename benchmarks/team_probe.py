@@ -59,6 +59,7 @@ def main():
                 ctx.synchronize()
                 ta.append(1e3 * (time.perf_counter() - t0))
             out["adj_ms"] = float(np.median(ta[1:]))
+            out["adj_phases_ms"] = {"setup": ctx.phase_ms(2), "wavefront": ctx.phase_ms(3), "finish": ctx.phase_ms(4)}
             out["adj_sha1"] = hashlib.sha1(d_gs.cpu().numpy().tobytes()).hexdigest()[:16]
         print(json.dumps(out), flush=True)
         del d_u0, d_f, d_u

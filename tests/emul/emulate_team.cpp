@@ -1,6 +1,6 @@
 // tests/emul/emulate_team.cpp -- TEST INFRASTRUCTURE.  A serial host emulation of the team kernel
-// (adtomo.jl_b200/csrc/kernels_fwd_team.cuh): it runs the kernel's OWN per-lane functions (tm_load_old, tm_prep,
-// tm_solve, tm_rows, tm_slot_live, v2_reskew_elem; compiled for the host) with the same plan, team shape,
+// (adtomo.jl_b200/csrc/kernels_fwd_team.cuh): it runs the kernel's OWN per-lane functions (tm_slot_setup, tm_load_old,
+// tm_prep, tm_solve, tm_rows, tm_slot_live, v2_reskew_elem; compiled for the host) with the same plan, team shape,
 // buffers, mailbox and round loop.  The CTAs of the team are advanced slot by slot by a scheduler (random, or
 // "upstream as far ahead as possible", or "downstream as close as possible") that only honours what the kernel
 // itself waits for: the CTA's level barrier, and the arrival of the tagged mailbox packets of a first-row slot.
@@ -29,6 +29,7 @@ static void sweep_t(const Plan2 &P, const TeamCfg &T, const double *rd, double *
         int a0, a1, lam, lam1;
         std::vector<int> pending;
         std::vector<double> sheets;
+        std::vector<TmSlotC> K;        // [slot][lane]: the kernel's per-sweep constants
         std::vector<TmOld> early;      // [slot][lane]: old values read one level ahead
         std::vector<char> has_early;   // [slot]
     };
@@ -37,42 +38,46 @@ static void sweep_t(const Plan2 &P, const TeamCfg &T, const double *rd, double *
         c.pending.clear();
         while (c.lam <= c.lam1 && c.pending.empty()) {
             for (int q = 0; q < (c.a1 - c.a0) * T.G32; q++) {
-                const int r = q / T.G32, g = q - r * T.G32, Ap = c.a0 + r;
+                const TmSlotC *K = &c.K[(size_t)q * 32];
                 bool has = false;
-                for (int lane = 0; lane < 32; lane++) {
-                    const int Cp = g * TM_LC + lane, Wp = c.lam - Ap - Cp;
-                    if (Wp >= 0 && Wp < P.dW && Cp < P.dC) has = true;
-                }
-                if (tm_slot_live(P, c.lam, Ap, g)) c.pending.push_back(q);
+                for (int lane = 0; lane < 32; lane++) has = has || tm_act(P, K[lane], c.lam);
+                bool live = tm_slot_live(P, K[0], 0, c.lam);
+                for (int lane = 1; lane < 32; lane++)
+                    if (tm_slot_live(P, K[lane], lane, c.lam) != live) err = NAN;      // must be warp-uniform
+                if (live) c.pending.push_back(q);
                 else {
                     if (has) err = NAN;               // a slot declared dead must not contain a node
                     for (int lane = 0; lane < 32; lane++)   // the kernel's dead-slot branch
-                        c.sheets[((c.lam & 1) * T.R + r) * T.SP + g * TM_LC + lane + 1] = INFINITY;
+                        c.sheets[(c.lam & 1) * T.R * T.SP + K[lane].sidx] = INFINITY;
                 }
             }
             if (c.pending.empty()) c.lam++;
         }
     };
     for (int t = 0; t < nC; t++) {
+        Cta &c = cta[t];
         int l0;
-        tm_rows(P, T, t, cta[t].a0, cta[t].a1, l0, cta[t].lam1);
-        cta[t].lam = l0;
-        cta[t].sheets.assign((size_t)2 * T.R * T.SP, INFINITY);
-        cta[t].early.resize((size_t)(cta[t].a1 - cta[t].a0) * T.G32 * 32);
-        cta[t].has_early.assign((size_t)(cta[t].a1 - cta[t].a0) * T.G32, 0);
-        fill(cta[t]);
+        tm_rows(P, T, t, c.a0, c.a1, l0, c.lam1);
+        c.lam = l0;
+        const int nslot = (c.a1 - c.a0) * T.G32;
+        c.sheets.assign((size_t)2 * T.R * T.SP, INFINITY);
+        c.K.resize((size_t)nslot * 32);
+        for (int q = 0; q < nslot; q++)
+            for (int lane = 0; lane < 32; lane++)
+                tm_slot_setup<SA, SW, SC>(P, T, t, c.a0, c.a1 - c.a0, lane, q, c.K[(size_t)q * 32 + lane]);
+        c.early.resize((size_t)nslot * 32);
+        c.has_early.assign((size_t)nslot, 0);
+        fill(c);
     }
     auto runnable = [&](int t, int q) {
         const Cta &c = cta[t];
-        const int r = q / T.G32, g = q - r * T.G32, Ap = c.a0 + r;
-        if (t == 0 || r != 0) return true;
         const tm_u64 *inbox = mbox.data() + (long long)t * 2 * T.mbStride;
         for (int lane = 0; lane < 32; lane++) {
-            int off, mb;
-            tm_addr<SA, SW, SC>(P, lane, c.lam, Ap, g, off, mb);
-            if (off < 0) continue;
+            const TmSlotC &K = c.K[(size_t)q * 32 + lane];
+            if (!(K.flags & TM_FIRST) || !tm_act(P, K, c.lam)) continue;
+            const long long mb = tm_off<SW>(P, K, c.lam) - K.slab;
             double v;
-            if (!tm_unpack(inbox[2 * (long long)mb], inbox[2 * (long long)mb + 1], base | (unsigned)c.lam, v)) return false;
+            if (!tm_unpack(inbox[2 * mb], inbox[2 * mb + 1], base | (unsigned)c.lam, v)) return false;
         }
         return true;
     };
@@ -95,22 +100,24 @@ static void sweep_t(const Plan2 &P, const TeamCfg &T, const double *rd, double *
         Cta &c = cta[t];
         const int q = c.pending[pick.second];
         c.pending.erase(c.pending.begin() + pick.second);
-        const int r = q / T.G32, g = q - r * T.G32, Ap = c.a0 + r, nrow = c.a1 - c.a0;
+        const tm_u64 *inbox = mbox.data() + (long long)t * 2 * T.mbStride;
+        tm_u64 *outbox = mbox.data() + (long long)(t + 1) * 2 * T.mbStride;
         TmPrep Q[32];
         for (int lane = 0; lane < 32; lane++) {
+            const TmSlotC &K = c.K[(size_t)q * 32 + lane];
             TmOld O;
             if (c.has_early[q]) O = c.early[(size_t)q * 32 + lane];
-            else tm_load_old<SA, SW, SC, CMP>(P, lane, c.lam, Ap, g, rd, fl, cmp, O);
-            tm_prep<SA, SW, SC>(P, T, t, lane, c.lam, r, Ap, g, O, mbox.data(), base, c.sheets.data(), Q[lane]);
+            else tm_load_old<SA, SW, SC, CMP>(P, K, c.lam, rd, fl, cmp, O);
+            tm_prep<SA, SW, SC>(P, T, K, c.lam, O, inbox, base, c.sheets.data(), Q[lane]);
         }
         c.has_early[q] = 0;
-        if (tm_slot_live(P, c.lam + 1, Ap, g)) {        // the prefetch: next level's old values are read NOW
+        if (tm_slot_live(P, c.K[(size_t)q * 32], 0, c.lam + 1)) {   // the prefetch: next level's old values are read NOW
             for (int lane = 0; lane < 32; lane++)
-                tm_load_old<SA, SW, SC, CMP>(P, lane, c.lam + 1, Ap, g, rd, fl, cmp, c.early[(size_t)q * 32 + lane]);
+                tm_load_old<SA, SW, SC, CMP>(P, c.K[(size_t)q * 32 + lane], c.lam + 1, rd, fl, cmp, c.early[(size_t)q * 32 + lane]);
             c.has_early[q] = 1;
         }
         for (int lane = 0; lane < 32; lane++)
-            tm_solve<OOP, CMP>(T, t, nrow, lane, c.lam, r, g, Q[lane], wr, h, err, mbox.data(), base, c.sheets.data());
+            tm_solve<OOP, CMP>(T, c.K[(size_t)q * 32 + lane], c.lam, Q[lane], wr, h, err, outbox, base, c.sheets.data());
         if (c.pending.empty()) { c.lam++; fill(c); }
     }
 }
