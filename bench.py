@@ -10,7 +10,8 @@ A "step" is one such evaluation over the batch.  N GPUs: weak scaling, 256 sourc
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
   python bench.py --impl reference ...                          CPU arm: the oracle port of the
-        reference algorithm on the host cores (the reference itself needs Julia+TF+Eigen)
+        reference algorithm on the host cores (pinned bit for bit to the reference's own C++, oracle/_ref;
+        the reference's adjoint is a sparse LU that is infeasible at this size, the port back-substitutes)
 
 Prints ONE JSON line (rank 0).
 """

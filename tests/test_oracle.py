@@ -1,12 +1,15 @@
 """CPU: pin the oracle (oracle/eikonal_oracle.c) before anything is compared against it.
 
-Pins: (1) the reference's own Python prototypes (tests/golden/*.npz, made by make_golden.py from
+Pins: (0) the reference's OWN C++ solvers compiled unmodified (oracle/_ref, bottom of this file): forward bit for
+bit, adjoint 1e-12 -- directly where /root/reference is mounted, and through the committed outputs
+tests/golden/ref_cpp.npz everywhere; (1) the reference's own Python prototypes (tests/golden/*.npz, made by make_golden.py from
 /root/reference/tests/Eikonal3D/prototype*.py); (2) the reference's matrix assembly solved with
 SciPy SuperLU (tests/ref_assembly.py); (3) finite-difference Taylor tests in the style of
 deps/CustomOps/*/gradtest.jl turned into assertions; (4) analytic homogeneous-medium solutions;
 (5) the discrete residual of tests/Eikonal3D/prototype.py:5-7.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -203,3 +206,97 @@ def test_fd_gradient_2d(oracle):
     gf, _ = oracle.eikonal2d_backward(2 * u, u, f, h, 29, 2)
     t = _taylor(y, f, rng.standard_normal(f.shape) * 0.1, gf)
     assert t[1][1] < t[0][1] / 30 and t[2][1] < t[1][1] / 30
+
+
+# ----------------------------------------------------------------------------------------------
+# Pin (0): the reference's OWN C++ solvers.  tests/golden/ref_cpp.npz holds outputs of
+# deps/CustomOps/Eikonal/Eikonal.h and Eikonal3D/Eikonal3D.cpp compiled unmodified (oracle/Makefile target
+# _ref/libref_eikonal.so, against oracle/eigen_stub) on the inputs of tests/golden/ref_cases.py.
+# Forward: bit for bit (hash of the bytes).  Adjoint: the reference factorises with a sparse LU (here: the
+# stub's dense LU), the oracle back-substitutes -- 1e-12 relative to max |grad|.
+# ----------------------------------------------------------------------------------------------
+sys.path.insert(0, G)
+import ref_cases  # noqa: E402
+
+REF_GOLD = os.path.join(G, "ref_cpp.npz")
+ADJ_RTOL = 1e-12
+
+
+def test_oracle_matches_reference_cpp_goldens_3d(oracle):
+    g = np.load(REF_GOLD)
+    for name, c in ref_cases.cases3d().items():
+        u, rounds, _ = oracle.eikonal3d_forward(c["u0"], c["f"], c["h"], c["tol"])
+        assert ref_cases.sha(u) == str(g[f"3d/{name}/u_sha256"]), name
+        np.testing.assert_array_equal(u.ravel()[::97], g[f"3d/{name}/u_sample"])
+        if f"3d/{name}/u" in g:
+            np.testing.assert_array_equal(u, g[f"3d/{name}/u"])
+        if c["grad_u"] is not None:
+            gu0, gf, _ = oracle.eikonal3d_backward(c["grad_u"], u, c["u0"], c["f"], c["h"])
+            np.testing.assert_array_equal(gu0, g[f"3d/{name}/grad_u0"])
+            ref_gf = g[f"3d/{name}/grad_f"]
+            assert np.abs(gf - ref_gf).max() <= ADJ_RTOL * np.abs(ref_gf).max(), name
+
+
+def test_oracle_matches_reference_cpp_goldens_2d(oracle):
+    g = np.load(REF_GOLD)
+    for name, c in ref_cases.cases2d().items():
+        u, _, conv = oracle.eikonal2d_forward(c["f"], c["h"], c["ix"], c["jx"])
+        assert conv
+        np.testing.assert_array_equal(u, g[f"2d/{name}/u"])
+        gf, _ = oracle.eikonal2d_backward(c["grad_u"], u, c["f"], c["h"], c["ix"], c["jx"])
+        ref_gf = g[f"2d/{name}/grad_f"]
+        assert np.abs(gf - ref_gf).max() <= ADJ_RTOL * np.abs(ref_gf).max(), name
+
+
+def _ref():
+    import oracle.ref as ref
+    if not ref.available():
+        pytest.skip("compiled reference (oracle/_ref) not present and /root/reference not mounted")
+    ref.build()
+    return ref
+
+
+def test_goldens_are_what_the_compiled_reference_produces():
+    """Where the reference can be compiled (this container), the committed fixture must be reproducible."""
+    ref = _ref()
+    g = np.load(REF_GOLD)
+    for name, c in ref_cases.cases3d().items():
+        if c["u0"].size > 30000:
+            continue
+        assert ref_cases.sha(ref.eikonal3d_forward(c["u0"], c["f"], c["h"], c["tol"])) == str(g[f"3d/{name}/u_sha256"])
+    for name, c in ref_cases.cases2d().items():
+        np.testing.assert_array_equal(ref.eikonal2d_forward(c["f"], c["h"], c["ix"], c["jx"]), g[f"2d/{name}/u"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_vs_compiled_reference_random(oracle, seed):
+    """Fresh random cases straight against the compiled reference: ragged shapes, several sources, all three
+    stopping rules (tol met, production tol, 20-round cap), adjoint on converged and unconverged fields."""
+    ref = _ref()
+    rng = np.random.default_rng(1000 + seed)
+    dims = tuple(int(x) for x in rng.integers(2, 14, 3))
+    f = 0.2 + 2.0 * rng.random(dims)
+    u0 = np.full(dims, 1000.0)
+    for _ in range(int(rng.integers(1, 4))):
+        u0[tuple(rng.integers(0, d) for d in dims)] = float(rng.random())
+    h = float(0.1 + rng.random())
+    for tol in (1e-6, 1e-3, 0.0, 1e9):
+        u_ref = ref.eikonal3d_forward(u0, f, h, tol)
+        u, _, _ = oracle.eikonal3d_forward(u0, f, h, tol)
+        np.testing.assert_array_equal(u, u_ref)
+        if tol in (1e-6, 1e9):
+            gu = rng.standard_normal(dims)
+            gu0_ref, gf_ref = ref.eikonal3d_backward(gu, u_ref, u0, f, h)
+            gu0, gf, _ = oracle.eikonal3d_backward(gu, u, u0, f, h)
+            np.testing.assert_array_equal(gu0, gu0_ref)
+            assert np.abs(gf - gf_ref).max() <= ADJ_RTOL * max(np.abs(gf_ref).max(), 1e-300)
+    shape = tuple(int(x) for x in rng.integers(2, 30, 2))
+    f2 = 0.2 + rng.random(shape)
+    ix, jx = int(rng.integers(0, shape[1])), int(rng.integers(0, shape[0]))
+    u_ref = ref.eikonal2d_forward(f2, h, ix, jx)
+    u, _, _ = oracle.eikonal2d_forward(f2, h, ix, jx)
+    np.testing.assert_array_equal(u, u_ref)
+    g2 = rng.standard_normal(shape)
+    gf_ref = ref.eikonal2d_backward(g2, u_ref, f2, h, ix, jx)
+    gf, _ = oracle.eikonal2d_backward(g2, u, f2, h, ix, jx)
+    assert np.abs(gf - gf_ref).max() <= ADJ_RTOL * max(np.abs(gf_ref).max(), 1e-300)
