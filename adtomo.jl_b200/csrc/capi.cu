@@ -585,7 +585,7 @@ static int fwd3d_team(adtomo_ctx *c, const Plan2Cache *pc, const TeamCfg &T, dou
     WS(c, "team_bufs", double, nb, bufs);
     WS(c, "team_flay", double, (size_t)2 * P.M, flay);
     WS(c, "team_where", int, 2 * (size_t)S, where);
-    WS(c, "team_sync", unsigned, (size_t)S * TM_SYNC_WORDS, sync);
+    WS(c, "team_sync", unsigned, (size_t)S * T.stride, sync);
     WS(c, "team_mbox", tm_u64, mbn, mbox);
     order = where + S;
     int pk = phase_begin(c, PH_CONVERT);
@@ -604,7 +604,7 @@ static int fwd3d_team(adtomo_ctx *c, const Plan2Cache *pc, const TeamCfg &T, dou
     }
     unsigned serial0 = c->team_serial;
     c->team_serial += need;
-    CK(cudaMemsetAsync(sync, 0, sizeof(unsigned) * (size_t)S * TM_SYNC_WORDS, c->stream));
+    CK(cudaMemsetAsync(sync, 0, sizeof(unsigned) * (size_t)S * T.stride, c->stream));
     const int eb = elem_grid(c, d.N);
     k2_f_to_layouts<<<eb, 256, 0, c->stream>>>(P, df, flay, flay + P.M);
     LAUNCHED(c, "k2_f_to_layouts");
@@ -758,7 +758,9 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
             int occ = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo_team<ANT>, ANT, 0) != cudaSuccess) { cudaGetLastError(); occ = 0; }
             const int budget = occ * c->num_sms / S;
-            int nC = c->adj_team > 0 ? std::min(c->adj_team, budget) : std::min(budget, 64);
+            // waves are short (N / #waves nodes): 64 CTAs are enough up to ~128^3 (64^3: 1.0 ms, 3.2 ms with 148), one CTA per
+            // SM pays from 256^3 on (7.6 -> 6.4 ms)
+            int nC = c->adj_team > 0 ? std::min(c->adj_team, budget) : std::min(budget, d.N > (1LL << 22) ? c->num_sms : 64);
             if (c->team_mode == 0 && c->adj_team == 0) nC = 1;
             if (nC >= 8 || (c->adj_team > 1 && nC > 1)) {
                 const int *tail0 = cnts + S, *nfree = cnts;

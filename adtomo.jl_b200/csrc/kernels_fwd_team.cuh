@@ -21,8 +21,15 @@
 // per warp and level): the CTAs form a systolic pipeline skewed by one L2 round trip per CTA.  A mailbox
 // has one slot per node of the boundary row (a slab of the skewed layout), so a producer can run
 // arbitrarily far ahead; tags only grow, across sweeps and across launches, so slots are never reset.
-// Team-wide barriers (a counter in global memory, with fences) separate the sweeps, the re-skews and
-// the rounds: ~13 per round.
+// Between sweeps the pipeline is NOT drained: every CTA owns fixed physical rows (its rank in the pipeline is
+// p or nC-1-p, by the sign of the sweep along A), re-skews its own slabs when the next sweep needs the other
+// layout, publishes "step k done" (fence + one word) and starts sweep k+1 as soon as both physical neighbours
+// have published step k: their rows (read as old downwind values) are final and re-skewed, and they no longer
+// read the mailbox a neighbour is about to refill.  Neighbours are therefore at most one sweep apart, which
+// is also why a re-skew may overwrite the buffer of the layout before last.  Sweeps that keep their direction
+// along A (4 of 8 in the reference order, 6 of 8 when A is the grid's k axis) follow each other through the
+// pipeline back to back.  ONE team-wide barrier per round (a counter in global memory, with fences) remains:
+// the stopping test needs the maximum over all CTAs.
 //
 // Lanes of a warp cover 32 consecutive columns C of ONE row A (a warp slot): at a fixed level these are
 // 32 consecutive doubles of one skewed row mu -- a 256-byte contiguous run for the node and for each of
@@ -46,7 +53,7 @@ namespace adtomo {
 
 constexpr int TM_LC = 32;          // columns per warp slot
 constexpr int TM_LEVEL_BITS = 12;  // packet tag = (sweep serial << 12) | (level + 1); nlev < 4095
-constexpr int TM_SYNC_WORDS = 8;   // per-source sync area (unsigned words): [0] barrier counter, [2..3],[4..5] err slots
+constexpr int TM_SYNC_HDR = 8;     // per-source sync area (unsigned words): [0] barrier counter, [2..3],[4..5] err slots, [8..8+nC) steps done
 
 struct TeamCfg {
     int nC;              // CTAs per source
@@ -54,6 +61,7 @@ struct TeamCfg {
     int G32;             // column groups of 32 per row
     long long mbStride;  // packets (16 bytes each) of one CTA's inbox = RS * PC (one slab of the skewed layout)
     int SP;              // pitch of a sheet row = 32 * G32 + 2 doubles
+    int stride;          // unsigned words of one source's sync area
 };
 
 #define TM_LDU(p) (*(p))           // old values: through L1 (see above)
@@ -98,10 +106,13 @@ inline void tm_mb_store(tm_u64 *slot, const tm_u64 p0, const tm_u64 p1) { slot[0
 inline void tm_mb_load(const tm_u64 *slot, tm_u64 &p0, tm_u64 &p1) { p0 = slot[0]; p1 = slot[1]; }
 #endif
 
-// rows [a0, a1) of team member t, first and last level at which one of them has a node
-EIK_HD void tm_rows(const Plan2 &P, const TeamCfg &T, const int t, int &a0, int &a1, int &lam0, int &lam1) {
-    a0 = t * T.R;
-    a1 = a0 + T.R < P.dA ? a0 + T.R : P.dA;
+// Team member p owns the PHYSICAL rows A in [p R, min((p+1) R, dA)).  In a sweep with sign SA along A these are
+// the rows A' in [a0, a1) counted in the sweep's direction; lam0 / lam1: first and last level at which one of
+// them has a node.  The member's upstream neighbour (whose packets it receives) is p-1 for SA > 0, p+1 otherwise.
+EIK_HD void tm_rows(const Plan2 &P, const TeamCfg &T, const int p, const int SA, int &a0, int &a1, int &lam0, int &lam1) {
+    const int lo = p * T.R, hi = lo + T.R < P.dA ? lo + T.R : P.dA;
+    a0 = SA > 0 ? lo : P.dA - hi;
+    a1 = SA > 0 ? hi : P.dA - lo;
     lam0 = a0;
     lam1 = a1 - 1 + P.dW - 1 + P.dC - 1;
 }
@@ -120,8 +131,9 @@ struct TmSlotC {
 enum { TM_COL = 1, TM_FIRST = 2, TM_LAST = 4, TM_RPOS = 8 };   // column exists; uA from the mailbox; packet to send; uA from the sheet
 
 template <int SA, int SW, int SC>
-EIK_HD void tm_slot_setup(const Plan2 &P, const TeamCfg &T, const int t, const int a0, const int nrow, const int lane,
+EIK_HD void tm_slot_setup(const Plan2 &P, const TeamCfg &T, const int p, const int a0, const int nrow, const int lane,
                           const int q, TmSlotC &K) {
+    const bool has_up = SA > 0 ? p > 0 : p < T.nC - 1, has_down = SA > 0 ? p < T.nC - 1 : p > 0;
     const int r = q / T.G32, g = q - r * T.G32;
     const int Ap = a0 + r, Cp = g * TM_LC + lane;
     const int A = SA > 0 ? Ap : P.dA - 1 - Ap;
@@ -131,8 +143,8 @@ EIK_HD void tm_slot_setup(const Plan2 &P, const TeamCfg &T, const int t, const i
     // mu + 1 = lam - Ap + 1 (SW > 0) or nmu - lam + Ap (SW < 0): one skewed row per level, uniform over the warp
     K.offc = K.slab + (SW > 0 ? 1 - Ap : P.nmu + Ap) * P.PC + C;
     K.sidx = r * T.SP + Cp + 1;
-    K.flags = (Cp < P.dC ? TM_COL : 0) | ((t > 0 && r == 0) ? TM_FIRST : 0) |
-              ((t < T.nC - 1 && r == nrow - 1) ? TM_LAST : 0) | (r > 0 ? TM_RPOS : 0);
+    K.flags = (Cp < P.dC ? TM_COL : 0) | ((has_up && r == 0) ? TM_FIRST : 0) |
+              ((has_down && r == nrow - 1) ? TM_LAST : 0) | (r > 0 ? TM_RPOS : 0);
 }
 
 // does the lane have a node at level lam?
@@ -191,7 +203,7 @@ EIK_HD void tm_prefetch_old(const Plan2 &P, const TmSlotC &K, const int lam, con
 // base = sweep serial << TM_LEVEL_BITS; a packet of level L carries tag base | (L + 1).
 // sheets: [2][R][SP] doubles, sheet (lam & 1) receives this level, the other one holds level lam-1:
 // column Cp at index Cp+1, index 0 = +inf.  The A neighbour of the CTA's first row comes from the mailbox
-// (inbox = mbox + t * 2 * mbStride, packets tagged base | lam) or is +inf (the grid's first row).
+// (inbox = mbox + p * 2 * mbStride, packets tagged base | lam) or is +inf (the grid's first row).
 // Host build: a packet that has not arrived yields NaN (the emulation's scheduler must prevent that).
 struct TmPrep {
     double a1, a2, a3, own, fv, ref;
@@ -236,7 +248,7 @@ EIK_HD void tm_prep(const Plan2 &P, const TeamCfg &T, const TmSlotC &K, const in
 }
 
 // The update (Eikonal3D.cpp:47-54), its store, its sheet entry (+inf when the lane has no node) and the packet
-// for the downstream CTA (outbox = mbox + (t + 1) * 2 * mbStride; written for EVERY node of the CTA's last row,
+// for the downstream CTA (outbox = the inbox of member p + 1 or p - 1; written for EVERY node of the CTA's last row,
 // changed or not: the consumer waits for it).
 template <bool OOP, bool CMP>
 EIK_HD void tm_solve(const TeamCfg &T, const TmSlotC &K, const int lam, const TmPrep &Q, double *wr, const double h,
@@ -285,6 +297,24 @@ __device__ __forceinline__ void tm_barrier(unsigned *ctr, unsigned &epoch, const
     __syncthreads();
 }
 
+// "Steps 1..step of this CTA are done": its rows are final (and re-skewed if the next sweep needs it).
+__device__ __forceinline__ void tm_publish(unsigned *done_p, const unsigned step) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(done_p), "r"(step) : "memory");
+    }
+}
+// Wait until both physical neighbours have published `step`.  The acquire loads also invalidate L1
+// (LDG.STRONG.GPU + CCTL.IVALL), which the L1 reads of the sweep rely on.
+__device__ __forceinline__ void tm_wait_neighbours(const unsigned *done, const int p, const int nC, const unsigned step) {
+    if (threadIdx.x == 0) {
+        if (p > 0) while (tm_ld_acquire(done + p - 1) < step) {}
+        if (p < nC - 1) while (tm_ld_acquire(done + p + 1) < step) {}
+    }
+    __syncthreads();
+}
+
 // One sweep of team member t.  A warp owns slots q = warp, warp + nw, ... for the whole sweep; the constants of
 // its first KS slots stay in registers, further slots (grids wider than KS x 512 columns per row) recompute them.
 template <int SA, int SW, int SC, bool OOP, bool CMP, int KS>
@@ -293,10 +323,10 @@ __device__ __forceinline__ void tm_sweep(const Plan2 &P, const TeamCfg &T, const
                                          double &err, tm_u64 *mbox, const unsigned base, double *sheets) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int a0, a1, lam0, lam1;
-    tm_rows(P, T, t, a0, a1, lam0, lam1);
+    tm_rows(P, T, t, SA, a0, a1, lam0, lam1);
     const int nrow = a1 - a0, nslot = nrow * T.G32;
     const tm_u64 *inbox = mbox + (long long)t * 2 * T.mbStride;
-    tm_u64 *outbox = mbox + (long long)(t + 1) * 2 * T.mbStride;
+    tm_u64 *outbox = mbox + (long long)(SA > 0 ? t + 1 : t - 1) * 2 * T.mbStride;
     for (int i = threadIdx.x; i < 2 * T.R * T.SP; i += blockDim.x) sheets[i] = v2_inf();
     TmSlotC K[KS];
 #pragma unroll
@@ -332,7 +362,7 @@ __device__ __forceinline__ void tm_sweep(const Plan2 &P, const TeamCfg &T, const
 
 // bufs: S x 3 x M doubles as in k_fwd3d_v2 (buffer 0 of every source: u0 in layout P; every slot that is
 // not a grid node: +inf in all three buffers).  grid = S x nC CTAs, ALL co-resident (cooperative launch).
-// sync: S x TM_SYNC_WORDS unsigned words, zero on entry.  mbox: S x nC inboxes of mbStride packets; no tag in
+// sync: S x T.stride unsigned words, zero on entry.  mbox: S x nC inboxes of mbStride packets; no tag in
 // it is >= (serial0 + 1) << TM_LEVEL_BITS (the host hands out serial ranges and clears the mailbox on wrap).
 // Dynamic shared memory: max(re-skew plane, two sheets of R x SP doubles); they are never live together.
 template <int NTMAX, int MINB, int KS>
@@ -345,44 +375,47 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_team(const Plan2 P, const
     extern __shared__ double plane[];
     __shared__ double red[32];
     const int src = blockIdx.x / T.nC, t = blockIdx.x - src * T.nC;
-    unsigned *sy = sync + (long long)src * TM_SYNC_WORDS;
-    unsigned *ctr = sy;
+    unsigned *sy = sync + (long long)src * T.stride;
+    unsigned *ctr = sy, *done = sy + TM_SYNC_HDR;
     unsigned long long *errslot = (unsigned long long *)(sy + 2);
     tm_u64 *mbox = mbox_all + (long long)src * T.nC * 2 * T.mbStride;
-    unsigned epoch = 0, serial = serial0;
+    unsigned epoch = 0, serial = serial0, step = 0;
     double *B3 = bufs + (long long)src * 3 * P.M;
     double *Bz = B3 + 2 * P.M;
-    const int A0 = t * T.R, A1 = A0 + T.R < P.dA ? A0 + T.R : P.dA;   // slabs this CTA re-skews
+    const int A0 = t * T.R, A1 = A0 + T.R < P.dA ? A0 + T.R : P.dA;   // the slabs this CTA owns (and re-skews)
     int o = 0, a = 1, r = 0;
     bool conv = false;
     while (r < max_rounds) {
         double err = 0.0;
         double *Bo = B3 + o * P.M, *Ba = B3 + a * P.M;
-        int state = 1;
+        int state = 1;                                // layout of the working field: sweep 0 is always on P
         double *w = Ba;
         for (int sw = 0; sw < 8; sw++) {
             const int sigma = P.sg[sw][1] * P.sg[sw][2];
-            if (sw > 0 && sigma != state) {
-                double *dst = state > 0 ? Bz : Ba;
-                tm_barrier(ctr, epoch, T.nC);         // the sweep that wrote w is complete everywhere
-                v2_reskew(P, w, dst, state, plane, A0, A1);
-                w = dst;
-                state = sigma;
-            }
-            tm_barrier(ctr, epoch, T.nC);             // previous sweep / re-skew complete everywhere
+            tm_wait_neighbours(done, t, T.nC, step);  // both neighbours finished the previous sweep (and its re-skew)
             serial++;
             const unsigned base = serial << TM_LEVEL_BITS;
 #define TM_CALL(a_, w_, c_, oop_, cmp_) \
     tm_sweep<a_, w_, c_, oop_, cmp_, KS>(P, T, t, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err, mbox, base, plane)
             V2_DISPATCH(P, sw, TM_CALL);
 #undef TM_CALL
+            if (sw < 7) {
+                const int next = P.sg[sw + 1][1] * P.sg[sw + 1][2];
+                if (next != state) {                  // the next sweep runs on the other layout: re-skew my slabs
+                    double *dst = state > 0 ? Bz : Ba;
+                    v2_reskew(P, w, dst, state, plane, A0, A1);
+                    w = dst;
+                    state = next;
+                }
+            }
+            tm_publish(done + t, ++step);
         }
         const double eb = v2_block_max(err, red);
         if (threadIdx.x == 0) atomicMax(errslot + (r & 1), (unsigned long long)__double_as_longlong(eb));   // eb >= 0
         tm_barrier(ctr, epoch, T.nC);
         const double e = __longlong_as_double((long long)__ldcg(errslot + (r & 1)));
         if (t == 0 && threadIdx.x == 0) {
-            errslot[(r + 1) & 1] = 0ULL;              // next round's slot: last read one round (>= 9 barriers) ago
+            errslot[(r + 1) & 1] = 0ULL;              // next round's slot: last read one round (>= 1 barrier) ago
             if (errs) errs[(long long)src * max_rounds + r] = e;
         }
         r++;
@@ -423,6 +456,7 @@ inline bool team_config(const Plan2 &P, int S, int max_ctas, int nwarps, int Rfo
     T.nC = (P.dA + R - 1) / R;
     T.mbStride = (long long)P.RS * P.PC;
     T.SP = TM_LC * T.G32 + 2;
+    T.stride = TM_SYNC_HDR + ((T.nC + 1) & ~1);
     return true;
 }
 

@@ -143,7 +143,10 @@ def emul_team():
     ((6, 16, 12), 1e-6, 5, 0, 1), ((12, 6, 16), 1e-4, 296, 0, 2), ((24, 19, 15), 1e-3, 7, 0, 0),
     ((33, 9, 10), 1e-6, 296, 3, 0), ((10, 35, 9), 1e-6, 296, 0, 1), ((9, 10, 41), 1e-6, 4, 0, 2),
     ((21, 21, 21), 1e-9, 296, 0, 0), ((9, 8, 70), 1e-6, 296, 0, 0), ((40, 5, 33), 1e-6, 296, 0, 2),
-    ((20, 40, 9), 1e-6, 1, 0, 0)])
+    ((20, 40, 9), 1e-6, 1, 0, 0),
+    # many CTAs (one row each), every scheduling policy: the CTAs of a team are in different sweeps most of the time
+    ((24, 19, 15), 1e-6, 296, 1, 0), ((24, 19, 15), 1e-6, 296, 1, 1), ((24, 19, 15), 1e-6, 296, 1, 2),
+    ((19, 24, 37), 1e-4, 296, 2, 0), ((37, 5, 40), 1e-6, 296, 4, 2), ((30, 30, 30), 1e-3, 11, 0, 1)])
 def test_emulated_team_bitexact(emul_team, oracle, dims, tol, max_ctas, rforce, policy):
     rng = np.random.default_rng(sum(dims) + 11)
     f = 0.5 + rng.random(dims)
