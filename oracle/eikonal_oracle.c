@@ -30,11 +30,17 @@
  * explicitly assembled matrix and against finite differences.
  *
  * PARITY PINNING: the reference stores no golden vectors for this path
- * (SURVEY 4, 8c).  Forward semantics are pinned against the reference's own
- * Python statements of the same sweeps (tests/Eikonal3D/prototype.py,
- * tests/Eikonal3D/prototype2d.py; fixtures in tests/golden made by
- * tests/golden/make_golden.py); the adjoint is pinned against SuperLU + FD.
- * The reference C++ itself cannot be compiled here (needs Eigen + TensorFlow).
+ * (SURVEY 4, 8c), so the pin is the reference's own code run here: its two
+ * solver files (Eikonal/Eikonal.h, Eikonal3D/Eikonal3D.cpp) compile UNMODIFIED
+ * against a small stub of the absent Eigen (oracle/eigen_stub, oracle/Makefile
+ * target _ref/libref_eikonal.so; the TensorFlow shims are not needed).  This
+ * restatement agrees with it bit for bit on forward solves (3D and 2D, every
+ * stopping rule) and to <= 1e-12 on adjoints (the reference factorises, we
+ * back-substitute): tests/test_oracle.py, directly where /root/reference is
+ * mounted and through the committed outputs tests/golden/ref_cpp.npz elsewhere.
+ * Second statements: the reference's Python prototypes of the sweeps
+ * (tests/Eikonal3D/prototype*.py -> tests/golden/proto*.npz), SciPy SuperLU on
+ * the explicitly assembled matrix, finite differences.
  */
 #include <math.h>
 #include <stdio.h>
