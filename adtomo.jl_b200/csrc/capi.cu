@@ -1175,6 +1175,11 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
             size_t budget = (size_t)(free_bytes() * 0.8);
             for (auto &kv : c->ws) budget += kv.second.second;   // what we already hold is reusable
             Sc = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, budget / per));
+            // When the batch must be chunked anyway, make a chunk a whole number of waves of the batch kernels
+            // (2 forward CTAs per SM, 1 adjoint CTA per SM): memory-sized chunks of 402 sources at 200x200x80 ran
+            // 296 resident forward CTAs plus a second wave that was one third full (267 instead of 333 solves/s/GPU).
+            const int wave = 2 * c->num_sms;
+            if (Sc < S && Sc > wave) Sc = (Sc / wave) * wave;
             c->chunk_cache[key] = Sc;
         }
     }

@@ -9,6 +9,7 @@ A "step" is one such evaluation over the batch.  N GPUs: weak scaling, 256 sourc
 (source sharding) + ONE all-reduce of the packed [gradient | misfit] buffer per step.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
+  python bench.py --config c4 --no-cpu ...                      BASELINE configs[3] (200x200x80, 2048 sources over the GPUs)
   python bench.py --impl reference ...                          CPU arm: the oracle port of the
         reference algorithm on the host cores (pinned bit for bit to the reference's own C++, oracle/_ref;
         the reference's adjoint is a sparse LU that is infeasible at this size, the port back-substitutes)
@@ -32,6 +33,7 @@ UNIT = "source-solves/s"
 GRID = (128, 128, 64)
 S_PER_GPU = 256
 E_RCV = 512
+C4_GRID, C4_SOURCES, C4_RCV = (200, 200, 80), 2048, 1024
 TOL = 1e-3
 H = 1.0
 
@@ -205,7 +207,13 @@ def run_ours(args):
             uid.copy_(torch.frombuffer(bytearray(A.Context.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         ctx.nccl_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
-    w = workload(world, rank, s_per_gpu=args.sources)
+    if args.config == "c4":
+        # BASELINE configs[3]: 200x200x80, 2048 sources in total sharded over the GPUs (strong scaling), 1024 receivers
+        if C4_SOURCES % world:
+            raise SystemExit(f"--config c4 needs a GPU count that divides {C4_SOURCES}")
+        w = workload(world, rank, s_per_gpu=C4_SOURCES // world, grid=C4_GRID, e_rcv=C4_RCV)
+    else:
+        w = workload(world, rank, s_per_gpu=args.sources)
     m, n, l = w["dims"]
     N = m * n * l
     S, E = len(w["sta"]), len(w["eve"])
@@ -334,9 +342,10 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.config == "c4" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3 inversion step: {m}x{n}x{l} grid, {S} sources/GPU x {world} GPU, {E} receivers, "
+        "config": {"workload": f"{args.config.upper()} inversion step: {m}x{n}x{l} grid, {S} sources/GPU x {world} GPU, {E} receivers, "
                                "GIL7+checkerboard(len 10, +-0.8 km/s) model, tol 1e-3, misfit + slowness gradient",
                    "sources_per_gpu": S, "rounds_mean": float(np.mean(rounds_dev)),
                    "l2": "inputs larger than L2 (travel-time fields of the batch: %.1f GB)" % (S * N * 8 / 1e9),
@@ -360,6 +369,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sources", type=int, default=S_PER_GPU, help="sources per GPU (default: the C3 batch of 256)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4"],
+                    help="c3 (default, the contract line): 128x128x64, 256 sources per GPU, weak scaling; "
+                         "c4: 200x200x80, 2048 sources in total sharded over the GPUs, strong scaling")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
