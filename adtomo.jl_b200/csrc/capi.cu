@@ -736,7 +736,8 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
     WS(c, "adj_queue", int, total, Q);
     WS(c, "adj_counters", int, 8 * (size_t)S, cnts);     // [0,S) free nodes, [S,2S) queue tails, [2S,3S) barrier counters, [4S,8S) push counters
     CK(cudaMemsetAsync(cnts, 0, sizeof(int) * 8 * S, c->stream));
-    const dim3 eg(std::min(elem_grid(c, d.N), 128), S);
+    // elementwise passes: (blocks per source, S) CTAs of 256 threads; few sources need more blocks each to fill the GPU
+    const dim3 eg(std::min(elem_grid(c, d.N), std::max(128, 16 * c->num_sms / S)), S);
     int pk = phase_begin(c, PH_ADJ_SETUP);
     k_adj3d_setup2<<<eg, 256, 0, c->stream>>>(dU, dU0, dG, UX, GD, dGU0, code, cnts, d, S);
     LAUNCHED(c, "k_adj3d_setup2");

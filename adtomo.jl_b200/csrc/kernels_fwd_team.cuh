@@ -181,16 +181,15 @@ EIK_HD void tm_load_old(const Plan2 &P, const TmSlotC &K, const int lam, const d
 }
 
 // L1 prefetch of what tm_load_old will read TM_PF levels ahead and no earlier level touches: the row of level
-// lam + TM_PF + 1 of this slab (dW, dC), the A-neighbour's row, slowness, round-start value.  One level ahead
-// covers an L2 hit; the fields of a 256^3 source (3 x 215 MB + mailboxes) do not fit L2 and a DRAM miss takes
-// longer than a level (measured level time 0.68 / 0.83 / 1.17 us at 64^3 / 128^3 / 256^3 with TM_PF = 1).
+// lam + TM_PF + 1 of this slab (dW, dC), the A-neighbour's row, slowness, round-start value.
+// Measured at 256^3: no prefetch 18.8 ms, distance 1 or 3 16.7 ms (one level ahead already covers the miss).
 #ifndef TM_PF
-#define TM_PF 3
+#define TM_PF 1
 #endif
 template <int SA, int SW, int SC, bool CMP>
 EIK_HD void tm_prefetch_old(const Plan2 &P, const TmSlotC &K, const int lam, const double *rd,
                             const double *__restrict__ fl, const double *cmp) {
-    if (!tm_act(P, K, lam + TM_PF)) return;
+    if (TM_PF <= 0 || !tm_act(P, K, lam + TM_PF)) return;
     const int offA = SA * P.RS * P.PC, offW = SW * P.PC;
     const int off = tm_off<SW>(P, K, lam + TM_PF);
     TM_PREFETCH(rd + off + offW);
@@ -320,13 +319,18 @@ __device__ __forceinline__ void tm_wait_neighbours(const unsigned *done, const i
 template <int SA, int SW, int SC, bool OOP, bool CMP, int KS>
 __device__ __forceinline__ void tm_sweep(const Plan2 &P, const TeamCfg &T, const int t, const double *rd, double *wr,
                                          const double *__restrict__ fl, const double *cmp, const double h,
-                                         double &err, tm_u64 *mbox, const unsigned base, double *sheets) {
+                                         double &err, tm_u64 *mbox, const unsigned base, double *sheets,
+                                         tm_u64 *volatile *s_box) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int a0, a1, lam0, lam1;
     tm_rows(P, T, t, SA, a0, a1, lam0, lam1);
     const int nrow = a1 - a0, nslot = nrow * T.G32;
-    const tm_u64 *inbox = mbox + (long long)t * 2 * T.mbStride;
-    tm_u64 *outbox = mbox + (long long)(SA > 0 ? t + 1 : t - 1) * 2 * T.mbStride;
+    // The two mailbox base pointers are per-sweep constants, but at 64 registers the compiler re-derived them
+    // (64-bit multiplies, ~30 instructions each) on every level: park them in shared memory, one LDS.64 per use.
+    if (threadIdx.x == 0) {
+        s_box[0] = mbox + (long long)t * 2 * T.mbStride;
+        s_box[1] = mbox + (long long)(SA > 0 ? t + 1 : t - 1) * 2 * T.mbStride;
+    }
     for (int i = threadIdx.x; i < 2 * T.R * T.SP; i += blockDim.x) sheets[i] = v2_inf();
     TmSlotC K[KS];
 #pragma unroll
@@ -342,8 +346,8 @@ __device__ __forceinline__ void tm_sweep(const Plan2 &P, const TeamCfg &T, const
             TmPrep Q;                                                                                 \
             tm_prefetch_old<SA, SW, SC, CMP>(P, K_, lam, rd, fl, cmp);                                \
             tm_load_old<SA, SW, SC, CMP>(P, K_, lam, rd, fl, cmp, O);                                 \
-            tm_prep<SA, SW, SC>(P, T, K_, lam, O, inbox, base, sheets, Q);                            \
-            tm_solve<OOP, CMP>(T, K_, lam, Q, wr, h, err, outbox, base, sheets);                      \
+            tm_prep<SA, SW, SC>(P, T, K_, lam, O, s_box[0], base, sheets, Q);                         \
+            tm_solve<OOP, CMP>(T, K_, lam, Q, wr, h, err, s_box[1], base, sheets);                    \
         }                                                                                             \
     } while (0)
     for (int lam = lam0; lam <= lam1; lam++) {
@@ -374,6 +378,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_team(const Plan2 P, const
                                                             const unsigned serial0) {
     extern __shared__ double plane[];
     __shared__ double red[32];
+    __shared__ tm_u64 *volatile s_box[2];
     const int src = blockIdx.x / T.nC, t = blockIdx.x - src * T.nC;
     unsigned *sy = sync + (long long)src * T.stride;
     unsigned *ctr = sy, *done = sy + TM_SYNC_HDR;
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_team(const Plan2 P, const
             serial++;
             const unsigned base = serial << TM_LEVEL_BITS;
 #define TM_CALL(a_, w_, c_, oop_, cmp_) \
-    tm_sweep<a_, w_, c_, oop_, cmp_, KS>(P, T, t, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err, mbox, base, plane)
+    tm_sweep<a_, w_, c_, oop_, cmp_, KS>(P, T, t, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err, mbox, base, plane, s_box)
             V2_DISPATCH(P, sw, TM_CALL);
 #undef TM_CALL
             if (sw < 7) {
