@@ -5,9 +5,10 @@
 // the transposed triangular system solved in decreasing-u order), so the result is the single-CTA kernel's,
 // bit for bit: a node's value depends only on its children's values, gathered in a fixed order.  With one
 // CTA per source a single large grid (BASELINE config C5) keeps one SM busy for ~100 ms at 256^3.  Here the
-// ready queue of a wave is split over the CTAs of a team; newly ready parents are appended to the queue
-// through a global counter (one atomic per warp and axis), and ONE team barrier (kernels_fwd_team.cuh:
-// tm_barrier, whose fences also invalidate L1) separates the waves.  The counter of wave w is D[w % 3]: it
+// ready queue of a wave is split over the CTAs of a team; newly ready parents are staged in shared memory
+// (one shared-memory atomic per warp and axis) and appended to the queue with ONE global atomic per CTA and
+// wave (one per warp and axis -- ~4000 on the same address per wave at 512^3 -- serialised in L2), and ONE
+// team barrier (kernels_fwd_team.cuh: tm_barrier, whose fences also invalidate L1) separates the waves.  The counter of wave w is D[w % 3]: it
 // counts the pushes of wave w relative to the wave's tail, is read by every CTA after barrier w, and is
 // cleared by CTA 0 after barrier w+1 -- when every CTA has read it -- for its next use in wave w+3.
 // grid = S x nC CTAs, all co-resident (cooperative launch).
@@ -25,6 +26,9 @@ __global__ void __launch_bounds__(NT) k_adj3d_topo_team(double2 *UX, const doubl
                                                         int *Q, const int *__restrict__ tail0, int *D,
                                                         const int *__restrict__ nfree, const Dims3 d, const int nC,
                                                         unsigned *bar, int *__restrict__ status) {
+    constexpr int CAP = 6144;                  // staged pushes per CTA and wave; beyond that: straight to the queue
+    __shared__ int s_stage[CAP];
+    __shared__ int s_n, s_base;
     const int l = d.l;
     const int nl = d.n * d.l;
     const int src = blockIdx.x / nC, t = blockIdx.x - src * nC;
@@ -39,6 +43,8 @@ __global__ void __launch_bounds__(NT) k_adj3d_topo_team(double2 *UX, const doubl
     const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
     while (head < tail) {
         int *Dw = Dsrc + waves % 3;
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
         for (int t0 = head + t * NT + (threadIdx.x & ~31); t0 < tail; t0 += nC * NT) {
             const int tq = t0 + (threadIdx.x & 31);
             int rp0 = -1, rp1 = -1, rp2 = -1;      // parents that became ready through this node
@@ -81,9 +87,13 @@ __global__ void __launch_bounds__(NT) k_adj3d_topo_team(double2 *UX, const doubl
         if (m) {                                                                           \
             const int leader = __ffs((int)m) - 1;                                          \
             int pos = 0;                                                                   \
-            if ((int)(threadIdx.x & 31) == leader) pos = tail + atomicAdd(Dw, __popc(m));  \
+            if ((int)(threadIdx.x & 31) == leader) pos = atomicAdd(&s_n, __popc(m));       \
             pos = __shfl_sync(0xffffffffu, pos, leader);                                   \
-            if (rp >= 0) q[pos + __popc(m & lt)] = rp;                                     \
+            if (rp >= 0) {                                                                 \
+                const int my = pos + __popc(m & lt);                                       \
+                if (my < CAP) s_stage[my] = rp;                                            \
+                else q[tail + atomicAdd(Dw, 1)] = rp;          /* staging full (rare) */   \
+            }                                                                              \
         }                                                                                  \
     }
             TOPO_PUSH(rp0)
@@ -91,6 +101,11 @@ __global__ void __launch_bounds__(NT) k_adj3d_topo_team(double2 *UX, const doubl
             TOPO_PUSH(rp2)
 #undef TOPO_PUSH
         }
+        __syncthreads();
+        const int staged = s_n < CAP ? s_n : CAP;
+        if (threadIdx.x == 0 && staged > 0) s_base = atomicAdd(Dw, staged);
+        __syncthreads();
+        for (int i = threadIdx.x; i < staged; i += NT) q[tail + s_base + i] = s_stage[i];
         tm_barrier(bar + src, epoch, nC);      // x values, counters and queue entries of this wave are visible
         const int pushed = __ldcg(Dw);
         if (t == 0 && threadIdx.x == 0) Dsrc[(waves + 2) % 3] = 0;   // wave w-1's counter: everyone read it before this barrier
