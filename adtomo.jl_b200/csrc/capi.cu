@@ -650,7 +650,10 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
     // Kernel choice.  Few sources (every source gets its own SM or cluster of SMs in ONE wave): the
     // level-major kernel, which puts 1024 threads (x cluster size) on a source.  A batch that oversubscribes
     // the SMs: the skewed-pencil kernel (two sources per SM, no shared-memory limit on the grid size).
-    // Few sources: a team of CTAs per source (every source gets >= 8 CTAs, or ADTOMO_TEAM=1).
+    // Few sources: a team of CTAs per source (every source gets >= 4 CTAs, or ADTOMO_TEAM=1).  Measured on the
+    // 128x128x64 checkerboard batch (benchmarks/batch_probe.py), forward ms for S = 8 / 16 / 37 / 64 / 100 / 148 sources:
+    // team 17.6 / 22.7 / 48.7 / 88.1 / 187 / 173, level-major (one SM per source) 82 / 82 / 96 / 96 / 96 / 87,
+    // skewed-pencil with one CTA per source 107 / 112 / 129 / 130 / 132 / 122.
     if (!c->force_v0 && !c->force_v1 && !c->force_v2 && !c->force_cluster && c->team_mode != 0) {
         const Plan2Cache *pt = get_plan_team(c, d.m, d.n, d.l);
         TeamCfg T;
@@ -658,7 +661,7 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
             // the CTA budget depends on the kernel variant and the shared memory, which depend on the team shape:
             // shape from the budget of the common case, then re-check the shape's own budget
             const int maxc = team_max_ctas(c, 2, pt->smem_bytes);
-            if (maxc > 0 && team_config(pt->plan, S, maxc, c->team_nt / 32, c->team_rows, T) && (T.nC >= 8 || c->team_mode == 1) &&
+            if (maxc > 0 && team_config(pt->plan, S, maxc, c->team_nt / 32, c->team_rows, T) && (T.nC >= 4 || c->team_mode == 1) &&
                 team_smem(pt, T) <= 100 * 1024 && S * T.nC <= team_max_ctas(c, team_ks(T, c->team_nt), team_smem(pt, T)))
                 return fwd3d_team(c, pt, T, dU, df, d, h, tol, max_rounds, S, d_rounds, d_errs, sp);
         }
