@@ -340,7 +340,6 @@ static size_t free_bytes() {
 // ---------------------------------------------------------------------------------------
 static constexpr int NT3 = 512;
 
-static constexpr int NT1 = 1024;
 static constexpr size_t SMEM_MAX_DYN = 227 * 1024 - 2048;
 
 static int get_plan(adtomo_ctx *c, int m, int n, int l, PlanCache **out) {
@@ -835,7 +834,7 @@ extern "C" int adtomo_eikonal3d_forward_batch(adtomo_ctx *c, double *u, const do
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     Dims3 d{m, n, l, (long long)m * n * l};
-    const double *df;
+    const double *df = nullptr;
     if ((rc = stage_in(c, "f", f, (size_t)d.N, loc, &df))) return rc;
     // chunk the sources so that host-staged batches fit the device
     int Sc = S;
@@ -917,7 +916,7 @@ extern "C" int adtomo_eikonal3d_backward_batch(adtomo_ctx *c, double *grad_u0, d
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     Dims3 d{m, n, l, (long long)m * n * l};
-    const double *df;
+    const double *df = nullptr;
     if ((rc = stage_in(c, "f", f, (size_t)d.N, loc, &df))) return rc;
     int Sc = S;
     {
@@ -1017,7 +1016,7 @@ extern "C" int adtomo_eikonal2d_forward_batch(adtomo_ctx *c, double *u, const do
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     const long long N2 = (long long)(m + 1) * (n + 1);
-    const double *df;
+    const double *df = nullptr;
     if ((rc = stage_in(c, "f", f, (size_t)N2, loc, &df))) return rc;
     int *dIX, *dJX, *dR;
     WS(c, "ix", int, S, dIX);
@@ -1067,7 +1066,7 @@ extern "C" int adtomo_eikonal2d_backward_batch(adtomo_ctx *c, double *grad_f, do
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     const long long N2 = (long long)(m + 1) * (n + 1);
-    const double *df, *dU, *dG;
+    const double *df = nullptr, *dU = nullptr, *dG = nullptr;
     if ((rc = stage_in(c, "f", f, (size_t)N2, loc, &df))) return rc;
     if ((rc = stage_in(c, "U", u, (size_t)S * N2, loc, &dU))) return rc;
     if ((rc = stage_in(c, "G", grad_u, (size_t)S * N2, loc, &dG))) return rc;
@@ -1158,7 +1157,7 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
                 return fail(ADTOMO_ERR_ARG, "receiver %d at (%g,%g,%g) outside the grid", e, p[0], p[1], p[2]);
         }
     }
-    const double *df, *dval, *drcv, *dobs, *dqua;
+    const double *df = nullptr, *dval = nullptr, *drcv = nullptr, *dobs = nullptr, *dqua = nullptr;
     const int *dptr, *didx;
     if ((rc = stage_in(c, "f", f, (size_t)d.N, loc, &df))) return rc;
     if ((rc = stage_in(c, "src_ptr", src_ptr, (size_t)S + 1, loc, &dptr))) return rc;
