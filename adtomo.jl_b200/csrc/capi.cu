@@ -86,6 +86,7 @@ struct adtomo_ctx {
     void *team_mbox_ptr = nullptr;
     size_t team_mbox_bytes = 0;
     int team_nt = 512;                          // 16 warps, <= 64 registers: two CTAs per SM
+    int coop_launch = 1;                        // cudaDevAttrCooperativeLaunch; without it the team kernels are never selected
     int adj_team = 0;                           // tuning aid: ADTOMO_ADJ_TEAM = CTAs per source of the adjoint wavefront (0: automatic, 1: single-CTA kernel)
 };
 
@@ -190,6 +191,13 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     c->force_cluster = fcl ? atoi(fcl) : 0;
     const char *tm = getenv("ADTOMO_TEAM");
     c->team_mode = tm ? atoi(tm) : -1;
+    {
+        // the team kernels spin on each other: they need all their CTAs co-resident (cooperative launch)
+        int coop = 0;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) { cudaGetLastError(); coop = 0; }
+        c->coop_launch = coop;
+        if (!coop) c->team_mode = 0;
+    }
     const char *atm = getenv("ADTOMO_ADJ_TEAM");
     c->adj_team = atm ? atoi(atm) : 0;
     const char *tmr = getenv("ADTOMO_TEAM_R");
@@ -764,7 +772,7 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
             // waves are short (N / #waves nodes): 64 CTAs are enough up to ~128^3 (64^3: 1.0 ms, 3.2 ms with 148), one CTA per
             // SM pays from 256^3 on (7.6 -> 6.4 ms)
             int nC = c->adj_team > 0 ? std::min(c->adj_team, budget) : std::min(budget, d.N > (1LL << 22) ? c->num_sms : 64);
-            if (c->team_mode == 0 && c->adj_team == 0) nC = 1;
+            if ((c->team_mode == 0 && c->adj_team == 0) || !c->coop_launch) nC = 1;
             if (nC >= 8 || (c->adj_team > 1 && nC > 1)) {
                 const int *tail0 = cnts + S, *nfree = cnts;
                 int *Dp = cnts + 4 * S;
