@@ -83,6 +83,7 @@ struct adtomo_ctx {
     // mailbox tags only grow (kernels_fwd_team.cuh): next free sweep serial; the mailbox is cleared when the
     // buffer changes or the 20-bit serial space is used up
     unsigned team_serial = 0;
+    unsigned team_serial_start = 0;             // testing aid (ADTOMO_TEAM_SERIAL0): first serial after the first allocation
     void *team_mbox_ptr = nullptr;
     size_t team_mbox_bytes = 0;
     int team_nt = 512;                          // 16 warps, <= 64 registers: two CTAs per SM
@@ -200,6 +201,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     }
     const char *atm = getenv("ADTOMO_ADJ_TEAM");
     c->adj_team = atm ? atoi(atm) : 0;
+    const char *ts0 = getenv("ADTOMO_TEAM_SERIAL0");      // testing aid: start the mailbox tag serial near its wrap
+    c->team_serial_start = ts0 ? (unsigned)strtoul(ts0, nullptr, 10) : 0u;
     const char *tmr = getenv("ADTOMO_TEAM_R");
     c->team_rows = tmr ? atoi(tmr) : 0;
     *out = c;
@@ -607,7 +610,9 @@ static int fwd3d_team(adtomo_ctx *c, const Plan2Cache *pc, const TeamCfg &T, dou
     if (need >= serial_max) return fail(ADTOMO_ERR_ARG, "max_rounds %d too large for the team kernel", max_rounds);
     if (c->team_mbox_ptr != (void *)mbox || c->team_mbox_bytes != c->ws["team_mbox"].second || c->team_serial + need >= serial_max) {
         CK(cudaMemsetAsync(mbox, 0, c->ws["team_mbox"].second, c->stream));
-        c->team_mbox_ptr = mbox; c->team_mbox_bytes = c->ws["team_mbox"].second; c->team_serial = 0;
+        c->team_mbox_ptr = mbox; c->team_mbox_bytes = c->ws["team_mbox"].second;
+        c->team_serial = (c->team_serial_start + need < serial_max) ? c->team_serial_start : 0;
+        c->team_serial_start = 0;
     }
     unsigned serial0 = c->team_serial;
     c->team_serial += need;
@@ -780,7 +785,9 @@ static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, cons
                 unsigned int *cnt32 = (unsigned int *)cnt;
                 Dims3 dd = d;
                 void *args[] = {&UX, &GD, &CM, &cnt32, &Q, &tail0, &Dp, &nfree, &dd, &nC, &bar, &d_status};
-                CK(cudaLaunchCooperativeKernel((const void *)k_adj3d_topo_team<ANT>, dim3(S * nC), dim3(ANT), args, 0, c->stream));
+                static const bool cap_small = getenv("ADTOMO_ADJ_CAP_SMALL") != nullptr;      // testing aid: staging overflow path
+                const void *akern = cap_small ? (const void *)k_adj3d_topo_team<ANT, 64> : (const void *)k_adj3d_topo_team<ANT>;
+                CK(cudaLaunchCooperativeKernel(akern, dim3(S * nC), dim3(ANT), args, 0, c->stream));
                 phase_end(c, pk);
                 LAUNCHED(c, "k_adj3d_topo_team");
                 pk = phase_begin(c, PH_ADJ_FINISH);

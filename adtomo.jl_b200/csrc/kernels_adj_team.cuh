@@ -20,13 +20,14 @@ namespace adtomo {
 
 // tail0: queue tails after k_adj3d_count2; D: S x 4 push counters (3 used), zero on entry; bar: S barrier
 // counters, zero on entry.
-template <int NT>
+// CAP: staged pushes per CTA and wave; beyond that a push goes straight to the queue (CAP = 64 exists only so that the
+// tests can exercise that path: ADTOMO_ADJ_CAP_SMALL=1).
+template <int NT, int CAP = 6144>
 __global__ void __launch_bounds__(NT) k_adj3d_topo_team(double2 *UX, const double2 *__restrict__ GD,
                                                         const unsigned short *__restrict__ CM, unsigned int *cnt32,
                                                         int *Q, const int *__restrict__ tail0, int *D,
                                                         const int *__restrict__ nfree, const Dims3 d, const int nC,
                                                         unsigned *bar, int *__restrict__ status) {
-    constexpr int CAP = 6144;                  // staged pushes per CTA and wave; beyond that: straight to the queue
     __shared__ int s_stage[CAP];
     __shared__ int s_n, s_base;
     const int l = d.l;
