@@ -8,6 +8,8 @@
 //  (4) packet hop: CTA A on one SM writes a tagged 16-byte packet (st.relaxed.gpu.v2.u64), CTA B on another SM
 //      spins on it (ld.relaxed.gpu.v2.u64) and answers; half the ping-pong round trip
 //  (5) STS -> __syncthreads -> LDS of another warp's value (the sheet hand-over)
+//  (6) the same ping-pong as (4) inside a thread-block cluster of 2: the producer writes the 8-byte token straight
+//      into the consumer's shared memory (st.shared::cluster via mapa), the consumer spins on its OWN shared memory
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -96,6 +98,37 @@ __global__ void k_hop(u64 *box, int iters, u64 *out, unsigned *smid) {
     }
     long long t1 = clock64();
     if (me == 0 && lane == 0) out[0] = (u64)(t1 - t0) / iters / 2;
+}
+
+// cluster of 2 CTAs, one warp each; lane 0 does the ping-pong with an 8-byte token in distributed shared memory
+__global__ void __cluster_dims__(2, 1, 1) k_hop_dsmem(int iters, u64 *out, unsigned *smid) {
+    __shared__ u64 slot;
+    unsigned rank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (threadIdx.x == 0) {
+        slot = 0;
+        unsigned s; asm("mov.u32 %0, %%smid;" : "=r"(s)); smid[rank] = s;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned; barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x == 0) {
+        const unsigned local = (unsigned)__cvta_generic_to_shared(&slot);
+        unsigned remote;
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(1u - rank));
+        long long t0 = clock64();
+        for (int i = 1; i <= iters; i++) {
+            u64 v;
+            if (rank == 0) {
+                asm volatile("st.relaxed.cluster.shared::cluster.u64 [%0], %1;" ::"r"(remote), "l"((u64)i) : "memory");
+                do { asm volatile("ld.relaxed.cluster.shared::cta.u64 %0, [%1];" : "=l"(v) : "r"(local) : "memory"); } while (v != (u64)i);
+            } else {
+                do { asm volatile("ld.relaxed.cluster.shared::cta.u64 %0, [%1];" : "=l"(v) : "r"(local) : "memory"); } while (v != (u64)i);
+                asm volatile("st.relaxed.cluster.shared::cluster.u64 [%0], %1;" ::"r"(remote), "l"((u64)i) : "memory");
+            }
+        }
+        long long t1 = clock64();
+        if (rank == 0) out[0] = (u64)(t1 - t0) / iters / 2;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned; barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 static u64 run_chase(size_t bytes, size_t stride, int mode, int iters, bool warm) {
@@ -198,7 +231,13 @@ int main() {
         CK(cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost));
         unsigned sm[2];
         CK(cudaMemcpy(sm, smid, 8, cudaMemcpyDeviceToHost));
-        printf(" \"packet_hop_cycles_one_way\": %llu, \"hop_between_sms\": [%u, %u]}\n", r[0], sm[0], sm[1]);
+        printf(" \"packet_hop_cycles_one_way\": %llu, \"hop_between_sms\": [%u, %u],\n", r[0], sm[0], sm[1]);
+        // (6) distributed shared memory inside a cluster of 2
+        k_hop_dsmem<<<2, 32>>>(iters, o, smid);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(sm, smid, 8, cudaMemcpyDeviceToHost));
+        printf(" \"dsmem_hop_cycles_one_way\": %llu, \"dsmem_hop_between_sms\": [%u, %u]}\n", r[0], sm[0], sm[1]);
     }
     return 0;
 }
