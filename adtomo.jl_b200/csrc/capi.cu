@@ -17,6 +17,7 @@
 #include "kernels_adj_topo.cuh"
 #include "kernels_fwd_v1.cuh"
 #include "kernels_fwd_v2.cuh"
+#include "kernels_fwd_v3.cuh"
 #include "kernels_fwd_team.cuh"
 #include "kernels_adj_team.cuh"
 #include "nccl_dyn.h"
@@ -65,6 +66,7 @@ struct adtomo_ctx {
     std::map<std::pair<long long, int>, int> chunk_cache;   // sources per chunk of the fused step, per (grid, batch)
     int v2_pairing = 1;                         // tuning aid: ADTOMO_V2_PAIRING=0 keeps sources in caller order
     std::map<std::tuple<const void *, int, const void *>, int *> v2_spent;   // rounds per source of earlier calls, per batch
+    int v3_mode = 1;                            // ADTOMO_V3: 1 (default) batch sweeps of kernels_fwd_v3.cuh with menu pitch, 2 same with run-time pitch, 0 the round-1 sweep loop (cross-check)
     int v2_occ = 0;                             // tuning aid: ADTOMO_V2_OCC caps the CTAs per SM of the skewed-pencil kernel
     std::vector<struct Plan2Cache *> plans2;    // skewed-pencil plans, one per grid shape
     // the +inf padding of the skewed-pencil field buffers is written once per (buffer, plan, sources)
@@ -96,6 +98,9 @@ struct Plan2Cache {
     bool ok;
     Plan2 plan;
     size_t smem_bytes;
+    // batch kernel (kernels_fwd_v3.cuh): compile-time row pitch of the instantiation (0: run-time pitch), slot table
+    int pct = 0, tabOffset = 0, maxPer = 0;
+    bool v3 = false;
 };
 
 struct PlanCache {
@@ -186,6 +191,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     c->v2_pairing = vpair ? atoi(vpair) : 1;
     const char *vocc = getenv("ADTOMO_V2_OCC");
     c->v2_occ = vocc ? atoi(vocc) : 0;
+    const char *v3m = getenv("ADTOMO_V3");
+    c->v3_mode = v3m ? atoi(v3m) : 1;
     const char *fvv = getenv("ADTOMO_FWD_VARIANT");
     c->fwd_variant = fvv ? atoi(fvv) : 0;
     const char *fcl = getenv("ADTOMO_FORCE_CLUSTER");
@@ -460,8 +467,23 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
     pc->m = m; pc->n = n; pc->l = l;
     // 16 warps: two CTAs per SM at 64 registers per thread
     const char *vw = getenv("ADTOMO_V2_WARPS");      // tuning aid
-    pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
+    if (c->v3_mode) {
+        pc->ok = v3_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024, &pc->pct, c->v3_mode == 1);
+        pc->v3 = pc->ok;
+    } else {
+        pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
+    }
     pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
+    if (pc->v3) {
+        pc->maxPer = v3_max_per_warp(pc->plan);
+        pc->tabOffset = (int)((pc->smem_bytes + 15) & ~(size_t)15);
+        pc->smem_bytes = pc->tabOffset + (sizeof(V3Slot) + sizeof(int)) * (size_t)(pc->plan.NT / 32) * pc->maxPer;
+        if (pc->smem_bytes > 100 * 1024) {           // table too large for two CTAs per SM: the round-1 sweep loop
+            pc->v3 = false;
+            pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
+            pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
+        }
+    }
     c->plans2.push_back(pc);
     return pc;
 }
@@ -482,8 +504,12 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     double *bufs, *flay;
     int *where, *order, *spent;
     const size_t nb = (size_t)S * 3 * P.M;
-    WS(c, "fwd2_bufs", double, nb, bufs);
-    WS(c, "fwd2_flay", double, (size_t)2 * P.M, flay);
+    // idle lanes of the batch kernel load (never store) up to v3_slack() doubles outside a buffer
+    const size_t slack = pc->v3 ? (size_t)v3_slack(P) : 0;
+    WS(c, "fwd2_bufs", double, nb + 2 * slack, bufs);
+    WS(c, "fwd2_flay", double, (size_t)2 * P.M + 2 * slack, flay);
+    bufs += slack;
+    flay += slack;
     WS(c, "fwd2_where", int, 2 * (size_t)S, where);
     order = where + S;
     // rounds each source of THIS batch needed last time (batch = plan, size, caller's rounds array)
@@ -536,14 +562,34 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
         kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol,    \
                                                                                  max_rounds, S, d_rounds, d_errs, where, order, spent); \
     } while (0)
-    if (P.NT <= 256) V2_LAUNCH(256, 2);
+#define V3_LAUNCH(PCT_)                                                                                                \
+    do {                                                                                                               \
+        auto kern = k_fwd3d_v3<512, 2, PCT_>;                                                                          \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                       \
+        int occ = 1;                                                                                                   \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));                           \
+        if (occ < 1) occ = 1;                                                                                          \
+        if (c->v2_occ > 0 && occ > c->v2_occ) occ = c->v2_occ;                                                         \
+        kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, pc->tabOffset, pc->maxPer, bufs, flay, flay + P.M, h, \
+                                                                                 tol, max_rounds, S, d_rounds, d_errs, where, order, spent); \
+    } while (0)
+    if (pc->v3 && P.NT <= 512) {
+        switch (pc->pct) {
+#define V3_CASE(pc_) case pc_: V3_LAUNCH(pc_); break;
+            V3_PC_MENU(V3_CASE)
+#undef V3_CASE
+            default: V3_LAUNCH(0); break;
+        }
+    }
+    else if (P.NT <= 256) V2_LAUNCH(256, 2);
     else if (P.NT <= 320) V2_LAUNCH(320, 2);
     else if (P.NT <= 384) V2_LAUNCH(384, 2);
     else if (P.NT <= 512) V2_LAUNCH(512, 2);
     else V2_LAUNCH(1024, 1);
+#undef V3_LAUNCH
 #undef V2_LAUNCH
     phase_end(c, pk);
-    LAUNCHED(c, "k_fwd3d_v2");
+    LAUNCHED(c, pc->v3 ? "k_fwd3d_v3" : "k_fwd3d_v2");
     pk = phase_begin(c, PH_CONVERT);
     k2_P_to_rowmajor<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, bufs, where, dU, order);
     phase_end(c, pk);

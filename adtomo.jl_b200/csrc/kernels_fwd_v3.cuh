@@ -1,0 +1,295 @@
+// kernels_fwd_v3.cuh -- 3D forward fast sweeping for BATCHES: the skewed-pencil layouts of
+// kernels_fwd_v2.cuh with a sweep loop rebuilt around the instruction count.
+//
+// Reference semantics: Eikonal3D.cpp:35-57 (one directional Gauss-Seidel sweep), :59-68 (the 8 sweeps of
+// a round), :71-88 (rounds until max|u - u_old| < tol, cap 20); level-by-level execution as in v2
+// (bit-identical to the serial sweep).
+//
+// Why.  ncu on k_fwd3d_v2 (profiles/r01_ncu_summary_v2.json): the kernel is bound by instruction issue,
+// not by HBM -- 95 G warp instructions for 403 M warp slots, i.e. ~206 executed SASS instructions per 32
+// node updates (cuobjdump of the round-1 build), of which only ~56 are the fp64 work of the exact update.
+// ~75 went into addresses (every neighbour offset is a run-time value: IADD3 + LEA + LEA.HI.X per load,
+// 64-bit buffer bases re-derived per slot) and ~25 into locating the warp's next slot (ballot + find-leading-one +
+// shuffle per slot on top of a window computation and a scan per level).  Skipping whole slots whose inputs did not
+// change (bit-exact) was measured first and saves only 5-9 % of the slot evaluations on the
+// bench model (benchmarks/skip_potential.c, profiles/r02_skip_potential.json): with tol = 1e-3 about 65 % of ALL
+// node evaluations still lower the node's value by a tiny amount, so almost every 4x8x8 box is touched in
+// every sweep.  The lever is instructions per slot:
+//   * the row pitch PC is a COMPILE-TIME constant taken from a small menu (the plan pads the rows; pad
+//     columns hold +inf like every other non-node slot), so the W and C neighbours are immediate
+//     offsets of ONE address register; only the A neighbours (slab stride) need a 64-bit add each;
+//   * warp slots are owned STATICALLY: the slots of a sweep are ranked by the level at which they become
+//     live and dealt cyclically to the warps (rank mod #warps).  Every slot is live for the same number of
+//     levels, so the live slots of a level are a contiguous range of ranks and every warp holds the same
+//     number of them (+-1): the balance of v2's per-level dealing without its per-slot search.  A warp's
+//     slots sit in a small shared-memory table (base offset, W' origin, first level); per level the warp
+//     advances a [head, tail) window over its own list;
+//   * loads of the warp's next slot are issued before the arithmetic of the current one, as in v2.
+#pragma once
+#include "kernels_fwd_v2.cuh"
+
+namespace adtomo {
+
+// Row pitches the batch kernel is compiled for (doubles; multiples of 8 so that a lane patch row is one
+// 64-byte run).  dC + 1 <= PC.  0 = run-time pitch (any grid).
+#define V3_PC_MENU(X) X(40) X(72) X(104) X(136) X(264)
+
+inline int v3_menu_pitch(int dC) {
+#define V3_PICK(pc_) if (dC + 1 <= pc_) return pc_;
+    V3_PC_MENU(V3_PICK)
+#undef V3_PICK
+    return 0;
+}
+
+// Table entry of a warp slot: base = rb * offRB + g * LC (added to the lane/level part of the node's offset),
+// meta = (sprime + V3_BIAS) | flags << 28 with sprime = rb * LA + SC * g * LC (W' origin) and flags = bit 0: last row
+// block of a grid with dA % LA != 0, bit 1: last column group with dC % LC != 0 (some lanes have no pencil there).
+struct V3Slot { int base, meta; };                // one int2 in shared memory
+constexpr int V3_BIAS = 1 << 20;
+
+// C' range (columns counted in the sweep's direction) of column group g
+template <int SC>
+EIK_HD void v3_cprange(const Plan2 &P, const int g, int &cpmin, int &cpmax) {
+    const int c_lo = g * V2_LC, c_hi = (g * V2_LC + V2_LC - 1 < P.dC - 1) ? g * V2_LC + V2_LC - 1 : P.dC - 1;
+    cpmin = SC > 0 ? c_lo : P.dC - 1 - c_hi;
+    cpmax = SC > 0 ? c_hi : P.dC - 1 - c_lo;
+}
+
+// Rank of warp slot (rb, g) in the order (first live level, g): the number of slots that come before it.
+template <int SC>
+EIK_HD int v3_rank(const Plan2 &P, const int rb, const int g, int &s_out) {
+    const int nrb = (P.dA + V2_LA - 1) / V2_LA;
+    int cm, cx;
+    v3_cprange<SC>(P, g, cm, cx);
+    const int s = V2_LA * rb + cm;
+    int r = 0;
+    for (int g2 = 0; g2 < P.G; g2++) {
+        int cm2, cx2;
+        v3_cprange<SC>(P, g2, cm2, cx2);
+        const int t = s - cm2;                    // row blocks rb2 of group g2 with V2_LA * rb2 < t start earlier
+        int c = t > 0 ? (t + V2_LA - 1) / V2_LA : 0;
+        if (c > nrb) c = nrb;
+        r += c;
+        if (g2 < g && t >= 0 && t % V2_LA == 0 && t / V2_LA < nrb) r++;    // same level, smaller g
+    }
+    s_out = s;
+    return r;
+}
+
+// Table entry of slot (rb, g) for a sweep with signs (SA, SW, SC); PC: row pitch.
+template <int SA, int SW, int SC>
+EIK_HD V3Slot v3_make_slot(const Plan2 &P, const int PC, const int rb, const int g) {
+    const int nrb = (P.dA + V2_LA - 1) / V2_LA;
+    V3Slot d;
+    d.base = rb * (V2_LA * (SA * P.RS - SW) * PC) + g * V2_LC;
+    const int flags = ((rb == nrb - 1 && P.dA % V2_LA) ? 1 : 0) | ((g == P.G - 1 && P.dC % V2_LC) ? 2 : 0);
+    d.meta = (rb * V2_LA + SC * g * V2_LC + V3_BIAS) | (flags << 28);
+    return d;
+}
+
+// levels a slot stays live after its first one (the longest slot; shorter ones just find no node)
+EIK_HD int v3_duration(const Plan2 &P) {
+    return (P.dA < V2_LA ? P.dA - 1 : V2_LA - 1) + (P.dC < V2_LC ? P.dC - 1 : V2_LC - 1) + P.dW - 1;
+}
+
+// Lane mask applied to V3Slot::meta: keeps the flag bits of the edges where this lane has NO pencil, so that a
+// flagged slot pushes the lane's W' far out of range.
+EIK_HD int v3_lane_mask(const Plan2 &P, const int la, const int lc) {
+    const int nrb = (P.dA + V2_LA - 1) / V2_LA;
+    const int bad = ((V2_LA * (nrb - 1) + la >= P.dA) ? 1 : 0) | ((V2_LC * (P.G - 1) + lc >= P.dC) ? 2 : 0);
+    return 0x0fffffff | (bad << 28);
+}
+
+// Node of a lane in slot d at level lam.  lamOff = L.offc + lam * SW * PC, lamWb = L.wqc + lam + V3_BIAS.
+// off: the slot of the lane's pencil position -- ALWAYS a loadable address: for a lane without a node it lies up to
+// LA + LC rows outside the slab or up to LA - 1 slabs outside the field (the buffers are allocated with
+// v3_slack() doubles on both sides); act: the position is a grid node.
+EIK_HD void v3_node(const Plan2 &P, const V3Slot &d, const int lamOff, const int lamWb, const int lmask, int &off, bool &act) {
+    const int wq = lamWb - (d.meta & lmask);
+    act = (unsigned)wq < (unsigned)P.dW;
+    off = lamOff + d.base;
+}
+
+// doubles of slack the field / slowness buffers need before and after (idle lanes load, never store, there)
+inline long long v3_slack(const Plan2 &P) { return (long long)(V2_LA + 1) * P.RS * P.PC; }
+
+// Loads of one node (same values as v2_load).  PCT: compile-time pitch or 0.  sAb: slab stride in bytes (RS * PC * 8).
+template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT>
+EIK_HD void v3_load(const Plan2 &P, const long long sAb, const int off, const bool act, const double *rd, const double *wr,
+                    const double *__restrict__ fl, const double *cmp, V2Vals &V) {
+    const int PC = PCT ? PCT : P.PC;
+    const int offW = SW * PC, offC = SW * PC + SC;
+    V.off = act ? off : -1;
+    const char *p = reinterpret_cast<const char *>(rd + off);
+#define V3_AT(ptr_, bytes_) (*reinterpret_cast<const double *>((ptr_) + (bytes_)))
+    V.own = V3_AT(p, 0);
+    V.fv = fl[off];
+    V.dW = V3_AT(p, offW * 8);
+    V.dC = V3_AT(p, offC * 8);
+    V.dA = V3_AT(p, SA * sAb);
+    const char *pu = OOP ? reinterpret_cast<const char *>(wr + off) : p;
+    V.uW = V3_AT(pu, -offW * 8);
+    V.uC = V3_AT(pu, -offC * 8);
+    V.uA = V3_AT(pu, -SA * sAb);
+#undef V3_AT
+    V.ref = CMP ? cmp[off] : 0.0;
+}
+
+#if defined(__CUDACC__)
+
+// Builds the CTA's slot table for a sweep: tab[w * maxPer + j] = j-th slot of warp w (ranks w, w + nw, ...),
+// tabS[same] = its first live level.
+template <int SA, int SW, int SC>
+__device__ __forceinline__ void v3_build_table(const Plan2 &P, const int PC, V3Slot *tab, int *tabS, const int maxPer) {
+    const int nw = blockDim.x >> 5;
+    const int nrb = (P.dA + V2_LA - 1) / V2_LA, nslots = nrb * P.G;
+    for (int idx = threadIdx.x; idx < nslots; idx += blockDim.x) {
+        const int rb = idx / P.G, g = idx - rb * P.G;
+        int s;
+        const int r = v3_rank<SC>(P, rb, g, s);
+        const int at = (r % nw) * maxPer + r / nw;
+        tab[at] = v3_make_slot<SA, SW, SC>(P, PC, rb, g);
+        tabS[at] = s;
+    }
+}
+
+template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT>
+__device__ __forceinline__ void v3_sweep(const Plan2 &P, V3Slot *tab, int *tabS, const int maxPer, const double *rd, double *wr,
+                                         const double *__restrict__ fl, const double *cmp, const double h, double &err) {
+    const int PC = PCT ? PCT : P.PC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const V2Lane L = v2_lane_setup<SA, SW, SC>(P, lane);      // P.PC == PC (the plan was built for this pitch)
+    const int lmask = v3_lane_mask(P, L.la, L.lc);
+    const int nslots = ((P.dA + V2_LA - 1) / V2_LA) * P.G;
+    const int cnt = warp < nslots ? (nslots - warp + nw - 1) / nw : 0;
+    const int dur = v3_duration(P);
+    const long long sAb = (long long)P.RS * PC * 8;
+    __syncthreads();     // the previous sweep (its field writes, its use of the table) is complete
+    v3_build_table<SA, SW, SC>(P, PC, tab, tabS, maxPer);
+    __syncthreads();
+    const int2 *mine = reinterpret_cast<const int2 *>(tab) + warp * maxPer;
+    const int *mineS = tabS + warp * maxPer;
+    int head = 0, tail = 0;
+    int sTail = cnt > 0 ? mineS[0] : 0x7fffffff;     // first level of the next slot to enter the window
+    int sHead = sTail;                                // first level of the oldest slot in the window
+    int lamOff = L.offc, lamWb = L.wqc + V3_BIAS;
+    for (int lam = 0; lam < P.nlev; lam++, lamOff += SW * PC, lamWb++) {
+        while (sTail <= lam) {
+            tail++;
+            sTail = tail < cnt ? mineS[tail] : 0x7fffffff;
+        }
+        while (head < tail && sHead + dur < lam) {
+            head++;
+            sHead = head < cnt ? mineS[head] : 0x7fffffff;
+        }
+        // The loads of the warp's next slot are issued before the current slot's arithmetic (software pipelining by
+        // hand; a two-register-set version without copies on the back edge spills at 64 registers).
+#define V3_LOAD(V_)                                                                              \
+    do {                                                                                         \
+        const int2 d2__ = *dp++;                                                                 \
+        V3Slot d__;                                                                              \
+        d__.base = d2__.x; d__.meta = d2__.y;                                                    \
+        int off__; bool act__;                                                                   \
+        v3_node(P, d__, lamOff, lamWb, lmask, off__, act__);                                     \
+        v3_load<SA, SW, SC, OOP, CMP, PCT>(P, sAb, off__, act__, rd, wr, fl, cmp, V_);           \
+    } while (0)
+        int left = tail - head;
+        if (left > 0) {
+            const int2 *dp = mine + head;
+            V2Vals V;
+            V3_LOAD(V);
+#pragma unroll 1
+            for (;;) {
+                V2Prep Q;
+                v2_prep(V, Q);                     // consumes V: its registers take the next slot's loads
+                if (--left > 0) V3_LOAD(V);
+                v2_solve<OOP, CMP>(Q, wr, h, err);
+                if (left <= 0) break;
+            }
+        }
+#undef V3_LOAD
+        __syncthreads();
+    }
+}
+
+// Same contract as k_fwd3d_v2 (buffers, order, rounds, errs, where, spent); the field and slowness buffers have
+// v3_slack() loadable doubles on both sides.  Dynamic shared memory: the re-skew plane (WCH x PS doubles) followed by
+// the slot table (nw x maxPer int2, then nw x maxPer int).
+template <int NTMAX, int MINB, int PCT>
+__global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const int tabOffset, const int maxPer, double *bufs,
+                                                          const double *__restrict__ fP, const double *__restrict__ fM,
+                                                          const double h, const double tol, const int max_rounds,
+                                                          const int S, int *__restrict__ rounds, double *__restrict__ errs,
+                                                          int *__restrict__ where, const int *__restrict__ order,
+                                                          int *__restrict__ spent) {
+    extern __shared__ double plane[];
+    __shared__ double red[32];
+    V3Slot *tab = reinterpret_cast<V3Slot *>(reinterpret_cast<char *>(plane) + tabOffset);
+    int *tabS = reinterpret_cast<int *>(tab + (blockDim.x >> 5) * maxPer);
+    for (int src = blockIdx.x; src < S; src += gridDim.x) {
+        double *B3 = bufs + (long long)src * 3 * P.M;
+        int o = 0, a = 1;          // layout P: round-start field, working field;  buffer 2: layout M
+        double *Bz = B3 + 2 * P.M;
+        int r = 0;
+        bool conv = false;
+        while (r < max_rounds) {
+            double err = 0.0;
+            double *Bo = B3 + o * P.M, *Ba = B3 + a * P.M;
+            int state = 1;                        // layout of the working field
+            double *w = Ba;
+            for (int sw = 0; sw < 8; sw++) {
+                const int sigma = P.sg[sw][1] * P.sg[sw][2];
+                if (sw > 0 && sigma != state) {
+                    double *dst = state > 0 ? Bz : Ba;
+                    __syncthreads();
+                    v2_reskew(P, w, dst, state, plane, 0, P.dA);
+                    w = dst;
+                    state = sigma;
+                }
+#define V3_CALL(a_, w_, c_, oop_, cmp_) \
+    v3_sweep<a_, w_, c_, oop_, cmp_, PCT>(P, tab, tabS, maxPer, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err)
+                V2_DISPATCH(P, sw, V3_CALL);
+#undef V3_CALL
+            }
+            const double e = v2_block_max(err, red);
+            if (threadIdx.x == 0 && errs) errs[(long long)order[src] * max_rounds + r] = e;
+            r++;
+            const int oo = o; o = a; a = oo;      // the result (in a) becomes next round's round-start field
+            if (__any_sync(0xffffffffu, e < tol)) { conv = true; break; }   // e is block-uniform
+        }
+        if (threadIdx.x == 0) {
+            if (rounds) rounds[order[src]] = conv ? r : -r;
+            spent[order[src]] = r;
+            {
+                unsigned sm__;
+                asm("mov.u32 %0, %%smid;" : "=r"(sm__));
+                spent[S + src] = (int)sm__;
+            }
+            where[src] = o;
+        }
+        __syncthreads();
+    }
+}
+
+#endif  // __CUDACC__
+
+// Plan of the batch kernel: v2's plan with the row pitch taken from the menu (PCT of the kernel instantiation to
+// launch is returned in *pct; 0 = no menu entry fits, run-time pitch).  The padded rows cost memory, not traffic.
+inline bool v3_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plane_bytes, int *pct, bool use_menu = true) {
+    if (!v2_build_plan(P, m, n, l, nwarps, plane_bytes)) return false;
+    const int pc = use_menu ? v3_menu_pitch(P.dC) : 0;
+    *pct = 0;
+    if (pc) {
+        const long long M = (long long)(P.dA + 2) * P.RS * pc;
+        if (M < (1LL << 31) - 4 * (long long)P.RS * pc) { P.PC = pc; P.M = M; *pct = pc; }
+    }
+    return true;
+}
+
+// slots per warp in the shared-memory table
+inline int v3_max_per_warp(const Plan2 &P) {
+    const int nslots = ((P.dA + V2_LA - 1) / V2_LA) * P.G, nw = P.NT / 32;
+    return (nslots + nw - 1) / nw;
+}
+
+}  // namespace adtomo
