@@ -135,6 +135,17 @@ EIK_HD void v3_load(const Plan2 &P, const long long sAb, const int off, const bo
     V.ref = CMP ? cmp[off] : 0.0;
 }
 
+// Re-skew index map for chunks with wc >= dC (every column wraps at most once): the same map as v2_reskew_index,
+// as lane/row parts that advance by constants.  Element (v, C): plane slot pl and slab offset go in layout sigma.
+//   cc = C (P) or dC-1-C (M);  wrapped = cc > v;  Wl = v - cc (+ wc);  pl = Wl * PS + C;  go = (w0 + Wl + cc + 1) * PC + C
+EIK_HD void v3_reskew_index(const Plan2 &P, const int sigma, const int w0, const int wc, const int v, const int C,
+                            int &pl, int &go) {
+    const int cc = sigma > 0 ? C : P.dC - 1 - C;
+    const bool wrapped = cc > v;
+    pl = (C - cc * P.PS) + v * P.PS + (wrapped ? wc * P.PS : 0);
+    go = (C + (w0 + 1) * P.PC) + v * P.PC + (wrapped ? wc * P.PC : 0);
+}
+
 #if defined(__CUDACC__)
 
 // Builds the CTA's slot table for a sweep: tab[w * maxPer + j] = j-th slot of warp w (ranks w, w + nw, ...),
@@ -150,6 +161,64 @@ __device__ __forceinline__ void v3_build_table(const Plan2 &P, const int PC, V3S
         const int at = (r % nw) * maxPer + r / nw;
         tab[at] = v3_make_slot<SA, SW, SC>(P, PC, rb, g);
         tabS[at] = s;
+    }
+}
+
+// Re-skew pass for chunks with wc >= dC: lane = column C, a warp takes virtual rows v = warp, warp + nw, ...; eight
+// elements in flight per thread, ~7 instructions per element (v2_reskew_pass: ~19, 18 % of the kernel's instructions).
+template <int PHASE>
+__device__ __forceinline__ void v3_reskew_pass(const Plan2 &P, const double *s, double *d, const int sigma,
+                                               double *plane, const int w0, const int wc) {
+    constexpr int U = 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int PC = P.PC, PS = P.PS, wrapG = wc * PC, wrapP = wc * PS;
+    for (int C = lane; C < P.dC; C += 32) {
+        const int cc = sigma > 0 ? C : P.dC - 1 - C;
+        const int plc = C - cc * PS, glc = C + (w0 + 1) * PC;
+        for (int v0 = warp; v0 < wc; v0 += U * nw) {
+            int pls[U], gos[U];
+            double x[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const int v = v0 + j * nw;
+                const bool wrapped = cc > v;
+                pls[j] = plc + v * PS + (wrapped ? wrapP : 0);
+                gos[j] = glc + v * PC + (wrapped ? wrapG : 0);
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                x[j] = 0.0;
+                if (v0 + j * nw < wc) x[j] = PHASE == 0 ? s[gos[j]] : plane[pls[j]];
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                if (v0 + j * nw < wc) {
+                    if (PHASE == 0) plane[pls[j]] = x[j];
+                    else d[gos[j]] = x[j];
+                }
+        }
+    }
+}
+
+// slabs A in [A0, A1); same contract as v2_reskew
+__device__ __forceinline__ void v3_reskew(const Plan2 &P, const double *src, double *dst, const int sigmaFrom,
+                                          double *plane, const int A0, const int A1) {
+    for (int A = A0; A < A1; A++) {
+        const double *s = src + (long long)(A + 1) * P.RS * P.PC;
+        double *d = dst + (long long)(A + 1) * P.RS * P.PC;
+        for (int w0 = 0; w0 < P.dW; w0 += P.WCH) {
+            const int wc = (P.dW - w0 < P.WCH) ? P.dW - w0 : P.WCH;
+            if (wc >= P.dC) {
+                v3_reskew_pass<0>(P, s, d, sigmaFrom, plane, w0, wc);
+                __syncthreads();
+                v3_reskew_pass<1>(P, s, d, -sigmaFrom, plane, w0, wc);
+            } else {
+                v2_reskew_pass<0>(P, s, d, sigmaFrom, plane, w0, wc);
+                __syncthreads();
+                v2_reskew_pass<1>(P, s, d, -sigmaFrom, plane, w0, wc);
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -242,7 +311,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const i
                 if (sw > 0 && sigma != state) {
                     double *dst = state > 0 ? Bz : Ba;
                     __syncthreads();
-                    v2_reskew(P, w, dst, state, plane, 0, P.dA);
+                    v3_reskew(P, w, dst, state, plane, 0, P.dA);
                     w = dst;
                     state = sigma;
                 }

@@ -15,6 +15,7 @@
 using namespace adtomo;
 
 static long long g_visits = 0;      // node updates of the last sweep
+static bool g_bad_reskew = false;
 static bool g_out_of_slack = false; // some lane (idle ones included) addressed beyond the slack around a buffer
 static int g_max_imbalance = 0;     // max over levels of (max - min) live slots per warp, over the whole solve
 
@@ -75,7 +76,18 @@ static void reskew(const Plan2 &P, const double *src, double *dst, int sigmaFrom
             const int wc = std::min(P.WCH, P.dW - w0);
             for (int phase = 0; phase < 2; phase++)
                 for (int v = 0; v < wc; v++)
-                    for (int C = 0; C < P.dC; C++) v2_reskew_elem(P, src, dst, sigmaFrom, plane.data(), slab, w0, wc, phase, v, C);
+                    for (int C = 0; C < P.dC; C++) {
+                        if (wc >= P.dC) {       // the kernel's fast index map: must agree with the general one
+                            int pl, go, pl2, go2;
+                            v3_reskew_index(P, phase == 0 ? sigmaFrom : -sigmaFrom, w0, wc, v, C, pl, go);
+                            v2_reskew_index(P, phase == 0 ? sigmaFrom : -sigmaFrom, w0, wc, v, C, pl2, go2);
+                            if (pl != pl2 || go != go2) g_bad_reskew = true;
+                            if (phase == 0) plane[pl] = src[slab + go];
+                            else dst[slab + go] = plane[pl];
+                        } else {
+                            v2_reskew_elem(P, src, dst, sigmaFrom, plane.data(), slab, w0, wc, phase, v, C);
+                        }
+                    }
         }
     }
 }
@@ -91,6 +103,7 @@ extern "C" int emul_v3_forward(double *u, const double *f, int m, int n, int l, 
     if (!v3_build_plan(P, m, n, l, warps, (size_t)plane_bytes, &pct, use_menu != 0)) return -1000;
     g_max_imbalance = 0;
     g_out_of_slack = false;
+    g_bad_reskew = false;
     std::vector<double> plane((size_t)P.WCH * P.PS);
     // the three field buffers are contiguous like in the kernel's workspace, with v3_slack() doubles on both sides
     // (idle lanes load from there); NaN in every slot that must never be USED
@@ -139,6 +152,7 @@ extern "C" int emul_v3_forward(double *u, const double *f, int m, int n, int l, 
         for (int j = 0; j < n; j++)
             for (int k = 0; k < l; k++) u[((long long)i * n + j) * l + k] = B[o][v2_offset_ijk(P, i, j, k, +1)];
     if (out) { out[0] = P.PC; out[1] = g_max_imbalance; out[2] = pct; }
+    if (g_bad_reskew) return -5000;
     if (g_out_of_slack) return -4000;
     if (bad_visits) return -3000;
     if (nfinite > 3 * P.N) return -2000;
