@@ -67,6 +67,7 @@ struct adtomo_ctx {
     int v2_pairing = 1;                         // tuning aid: ADTOMO_V2_PAIRING=0 keeps sources in caller order
     std::map<std::tuple<const void *, int, const void *>, int *> v2_spent;   // rounds per source of earlier calls, per batch
     int v3_mode = 1;                            // ADTOMO_V3: 1 (default) batch sweeps of kernels_fwd_v3.cuh with menu pitch, 2 same with run-time pitch, 0 the round-1 sweep loop (cross-check)
+    int v3_staged = 1;                          // ADTOMO_V3_STAGED: cp.async look-ahead through shared memory (0: register pipelining only)
     int v2_occ = 0;                             // tuning aid: ADTOMO_V2_OCC caps the CTAs per SM of the skewed-pencil kernel
     std::vector<struct Plan2Cache *> plans2;    // skewed-pencil plans, one per grid shape
     // the +inf padding of the skewed-pencil field buffers is written once per (buffer, plan, sources)
@@ -193,6 +194,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     c->v2_occ = vocc ? atoi(vocc) : 0;
     const char *v3m = getenv("ADTOMO_V3");
     c->v3_mode = v3m ? atoi(v3m) : 1;
+    const char *v3s = getenv("ADTOMO_V3_STAGED");
+    c->v3_staged = v3s ? atoi(v3s) : 1;
     const char *fvv = getenv("ADTOMO_FWD_VARIANT");
     c->fwd_variant = fvv ? atoi(fvv) : 0;
     const char *fcl = getenv("ADTOMO_FORCE_CLUSTER");
@@ -476,6 +479,7 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
     pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
     if (pc->v3) {
         pc->maxPer = v3_max_per_warp(pc->plan);
+        if (pc->pct) pc->smem_bytes = std::max(pc->smem_bytes, (size_t)V3_STAGE_BYTES_PER_WARP * (pc->plan.NT / 32));   // cp.async staging aliases the plane
         pc->tabOffset = (int)((pc->smem_bytes + 15) & ~(size_t)15);
         pc->smem_bytes = pc->tabOffset + (sizeof(V3Slot) + sizeof(int)) * (size_t)(pc->plan.NT / 32) * pc->maxPer;
         if (pc->smem_bytes > 100 * 1024) {           // table too large for two CTAs per SM: the round-1 sweep loop
@@ -562,9 +566,9 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
         kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol,    \
                                                                                  max_rounds, S, d_rounds, d_errs, where, order, spent); \
     } while (0)
-#define V3_LAUNCH(PCT_)                                                                                                \
+#define V3_LAUNCH(PCT_, STG_)                                                                                          \
     do {                                                                                                               \
-        auto kern = k_fwd3d_v3<512, 2, PCT_>;                                                                          \
+        auto kern = k_fwd3d_v3<512, 2, PCT_, STG_>;                                                                        \
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                       \
         int occ = 1;                                                                                                   \
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));                           \
@@ -575,10 +579,10 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     } while (0)
     if (pc->v3 && P.NT <= 512) {
         switch (pc->pct) {
-#define V3_CASE(pc_) case pc_: V3_LAUNCH(pc_); break;
+#define V3_CASE(pc_) case pc_: if (c->v3_staged) V3_LAUNCH(pc_, true); else V3_LAUNCH(pc_, false); break;
             V3_PC_MENU(V3_CASE)
 #undef V3_CASE
-            default: V3_LAUNCH(0); break;
+            default: V3_LAUNCH(0, false); break;
         }
     }
     else if (P.NT <= 256) V2_LAUNCH(256, 2);

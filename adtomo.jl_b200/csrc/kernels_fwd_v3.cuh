@@ -281,10 +281,116 @@ __device__ __forceinline__ void v3_sweep(const Plan2 &P, V3Slot *tab, int *tabS,
     }
 }
 
+// ---- staged variant: the eight values of a node travel global -> shared memory with cp.async, two warp slots ahead ----
+// ncu on the register-pipelined sweep (profiles/r02_ncu_summary_v3a.json): 32 % of the resident warps wait on a load
+// (long scoreboard at the first use of the next slot's values) although those loads were issued a whole solve earlier:
+// with ~7 of 8 warps per scheduler needed in the arithmetic to fill the issue slots, one slot of look-ahead is not
+// enough, and a second register set does not fit 64 registers.  Here the look-ahead lives in shared memory (the re-skew
+// plane is idle during a sweep): 2 stages x 8 values x 32 lanes x 8 B = 4 KB per warp, lane-private, so cp.async's
+// per-thread completion (wait_group) is the only synchronisation.
+template <int SOFF, int GOFF>
+__device__ __forceinline__ void v3_cp8(const unsigned s, const void *g) {
+    asm volatile("cp.async.ca.shared.global [%0 + %2], [%1 + %3], 8;" ::"r"(s), "l"(g), "n"(SOFF), "n"(GOFF) : "memory");
+}
+__device__ __forceinline__ void v3_cp8r(const unsigned s, const void *g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void v3_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void v3_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int V3_STAGE_BYTES_PER_WARP = 2 * 8 * 32 * 8;
+
+template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT>
+__device__ __forceinline__ void v3_sweep_staged(const Plan2 &P, V3Slot *tab, int *tabS, const int maxPer, double *stage,
+                                                const double *rd, double *wr, const double *__restrict__ fl,
+                                                const double *cmp, const double h, double &err) {
+    static_assert(PCT != 0, "the staged sweep needs a compile-time pitch");
+    constexpr int PC = PCT;
+    constexpr int offW8 = SW * PC * 8, offC8 = (SW * PC + SC) * 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const V2Lane L = v2_lane_setup<SA, SW, SC>(P, lane);
+    const int lmask = v3_lane_mask(P, L.la, L.lc);
+    const int nslots = ((P.dA + V2_LA - 1) / V2_LA) * P.G;
+    const int cnt = warp < nslots ? (nslots - warp + nw - 1) / nw : 0;
+    const int dur = v3_duration(P);
+    const long long sAb = (long long)SA * P.RS * PC * 8;
+    __syncthreads();     // the previous sweep / re-skew (field writes, table, plane) is complete
+    v3_build_table<SA, SW, SC>(P, PC, tab, tabS, maxPer);
+    __syncthreads();
+    const int2 *mine = reinterpret_cast<const int2 *>(tab) + warp * maxPer;
+    const int *mineS = tabS + warp * maxPer;
+    double *sp = stage + warp * (V3_STAGE_BYTES_PER_WARP / 8) + lane;              // value k of stage d: sp[(d * 8 + k) * 32]
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(sp);
+    int head = 0, tail = 0;
+    int sTail = cnt > 0 ? mineS[0] : 0x7fffffff;
+    int sHead = sTail;
+    int lamOff = L.offc, lamWb = L.wqc + V3_BIAS;
+    for (int lam = 0; lam < P.nlev; lam++, lamOff += SW * PC, lamWb++) {
+        while (sTail <= lam) {
+            tail++;
+            sTail = tail < cnt ? mineS[tail] : 0x7fffffff;
+        }
+        while (head < tail && sHead + dur < lam) {
+            head++;
+            sHead = head < cnt ? mineS[head] : 0x7fffffff;
+        }
+        // asks for the eight values of the warp's next slot (stage par_: 0 or 2048 bytes); off_ receives V.off
+#define V3_ISSUE(par_, off_)                                                                     \
+    do {                                                                                         \
+        const int2 d2__ = *dp++;                                                                 \
+        V3Slot d__;                                                                              \
+        d__.base = d2__.x; d__.meta = d2__.y;                                                    \
+        int off__; bool act__;                                                                   \
+        v3_node(P, d__, lamOff, lamWb, lmask, off__, act__);                                     \
+        off_ = act__ ? off__ : -1;                                                               \
+        const unsigned s__ = sb + (par_);                                                        \
+        const char *p__ = reinterpret_cast<const char *>(rd + off__);                            \
+        const char *pu__ = OOP ? reinterpret_cast<const char *>(wr + off__) : p__;               \
+        v3_cp8<0 * 256, 0>(s__, p__);                                                            \
+        v3_cp8r(s__ + 1 * 256, fl + off__);                                                      \
+        v3_cp8<2 * 256, offW8>(s__, p__);                                                        \
+        v3_cp8<3 * 256, offC8>(s__, p__);                                                        \
+        v3_cp8r(s__ + 4 * 256, p__ + sAb);                                                       \
+        v3_cp8<5 * 256, -offW8>(s__, pu__);                                                      \
+        v3_cp8<6 * 256, -offC8>(s__, pu__);                                                      \
+        v3_cp8r(s__ + 7 * 256, pu__ - sAb);                                                      \
+        v3_cp_commit();                                                                          \
+    } while (0)
+        int left = tail - head;
+        if (left > 0) {
+            const int2 *dp = mine + head;
+            int off0, off1 = -1;               // V.off of the two slots in flight (oldest first)
+            V3_ISSUE(0, off0);
+            if (left > 1) V3_ISSUE(2048, off1);
+            int par = 0;
+#pragma unroll 1
+            for (;;) {
+                if (left > 1) v3_cp_wait<1>(); else v3_cp_wait<0>();
+                V2Vals V;
+                const double *q = sp + par * 8;              // par = 0 / 32: stage 0 / 1 (8 values x 32 lanes apart)
+                V.own = q[0 * 32]; V.fv = q[1 * 32]; V.dW = q[2 * 32]; V.dC = q[3 * 32];
+                V.dA = q[4 * 32]; V.uW = q[5 * 32]; V.uC = q[6 * 32]; V.uA = q[7 * 32];
+                V.off = off0;
+                V.ref = CMP ? cmp[off0 < 0 ? 0 : off0] : 0.0;      // used last, after the solve
+                V2Prep Q;
+                v2_prep(V, Q);                 // the stage is free again: its values sit in registers
+                off0 = off1;
+                if (left > 2) V3_ISSUE(par * 64, off1);
+                v2_solve<OOP, CMP>(Q, wr, h, err);
+                par ^= 32;
+                if (--left <= 0) break;
+            }
+        }
+#undef V3_ISSUE
+        __syncthreads();
+    }
+}
+
 // Same contract as k_fwd3d_v2 (buffers, order, rounds, errs, where, spent); the field and slowness buffers have
 // v3_slack() loadable doubles on both sides.  Dynamic shared memory: the re-skew plane (WCH x PS doubles) followed by
 // the slot table (nw x maxPer int2, then nw x maxPer int).
-template <int NTMAX, int MINB, int PCT>
+template <int NTMAX, int MINB, int PCT, bool STG>
 __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const int tabOffset, const int maxPer, double *bufs,
                                                           const double *__restrict__ fP, const double *__restrict__ fM,
                                                           const double h, const double tol, const int max_rounds,
@@ -315,8 +421,13 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const i
                     w = dst;
                     state = sigma;
                 }
-#define V3_CALL(a_, w_, c_, oop_, cmp_) \
-    v3_sweep<a_, w_, c_, oop_, cmp_, PCT>(P, tab, tabS, maxPer, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err)
+#define V3_CALL(a_, w_, c_, oop_, cmp_)                                                                                  \
+    do {                                                                                                                 \
+        if constexpr (STG && PCT != 0)                                                                                   \
+            v3_sweep_staged<a_, w_, c_, oop_, cmp_, PCT>(P, tab, tabS, maxPer, plane, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
+        else                                                                                                             \
+            v3_sweep<a_, w_, c_, oop_, cmp_, PCT>(P, tab, tabS, maxPer, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
+    } while (0)
                 V2_DISPATCH(P, sw, V3_CALL);
 #undef V3_CALL
             }

@@ -348,6 +348,7 @@ def run_ours(args):
         "config": {"workload": f"{args.config.upper()} inversion step: {m}x{n}x{l} grid, {S} sources/GPU x {world} GPU, {E} receivers, "
                                "GIL7+checkerboard(len 10, +-0.8 km/s) model, tol 1e-3, misfit + slowness gradient",
                    "sources_per_gpu": S, "rounds_mean": float(np.mean(rounds_dev)),
+                   "rounds_hist": {str(int(k)): int(v) for k, v in zip(*np.unique(np.abs(rounds_dev), return_counts=True))},
                    "l2": "inputs larger than L2 (travel-time fields of the batch: %.1f GB)" % (S * N * 8 / 1e9),
                    "parallelism": f"source-shard x{world}" + (" + 1 NCCL all-reduce of N+1 fp64 per step (adtomo_nccl_allreduce_sum)" if world > 1 else "")},
         "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
