@@ -68,6 +68,8 @@ def load_library():
     L.adtomo_last_phase_ms.argtypes = [_vp, c_int]
     L.adtomo_launch_count.restype = ctypes.c_longlong
     L.adtomo_launch_count.argtypes = [_vp]
+    L.adtomo_last_forward_kernel.restype = ctypes.c_char_p
+    L.adtomo_last_forward_kernel.argtypes = [_vp]
     L.adtomo_selftest_sqrt.restype = c_int
     L.adtomo_selftest_sqrt.argtypes = [_vp, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_longlong)]
     L.adtomo_eikonal2d_forward.restype = c_int
@@ -154,6 +156,10 @@ class Context:
     @property
     def stream(self):
         return int(self._lib.adtomo_stream(self.handle))
+
+    def last_kernel(self):
+        """Name of the 3D forward sweep kernel of the last call."""
+        return self._lib.adtomo_last_forward_kernel(self.handle).decode()
 
     @property
     def last_kernel_ms(self):

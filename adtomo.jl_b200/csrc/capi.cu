@@ -66,8 +66,9 @@ struct adtomo_ctx {
     std::map<std::pair<long long, int>, int> chunk_cache;   // sources per chunk of the fused step, per (grid, batch)
     int v2_pairing = 1;                         // tuning aid: ADTOMO_V2_PAIRING=0 keeps sources in caller order
     std::map<std::tuple<const void *, int, const void *>, int *> v2_spent;   // rounds per source of earlier calls, per batch
+    const char *last_fwd_kernel = "";           // name of the last 3D forward sweep kernel launched (adtomo_last_forward_kernel)
     int v3_mode = 1;                            // ADTOMO_V3: 1 (default) batch sweeps of kernels_fwd_v3.cuh with menu pitch, 2 same with run-time pitch, 0 the round-1 sweep loop (cross-check)
-    int v3_staged = 0;                          // ADTOMO_V3_STAGED: cp.async look-ahead through shared memory (0: register pipelining only)
+    int v3_staged = -1;                         // ADTOMO_V3_STAGED: cp.async look-ahead through shared memory: -1 automatic (one CTA per SM), 0 never, 1 always
     int v2_occ = 0;                             // tuning aid: ADTOMO_V2_OCC caps the CTAs per SM of the skewed-pencil kernel
     std::vector<struct Plan2Cache *> plans2;    // skewed-pencil plans, one per grid shape
     // the +inf padding of the skewed-pencil field buffers is written once per (buffer, plan, sources)
@@ -102,7 +103,6 @@ struct Plan2Cache {
     // batch kernel (kernels_fwd_v3.cuh): compile-time row pitch of the instantiation (0: run-time pitch), slot table
     int pct = 0, tabOffset = 0, maxPer = 0;
     bool v3 = false;
-    int rsk2 = 0;       // re-skew with cp.async and two plane stages (the plane then holds 2 x WCH x PS doubles)
 };
 
 struct PlanCache {
@@ -196,7 +196,7 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     const char *v3m = getenv("ADTOMO_V3");
     c->v3_mode = v3m ? atoi(v3m) : 1;
     const char *v3s = getenv("ADTOMO_V3_STAGED");
-    c->v3_staged = v3s ? atoi(v3s) : 0;
+    c->v3_staged = v3s ? atoi(v3s) : -1;
     const char *fvv = getenv("ADTOMO_FWD_VARIANT");
     c->fwd_variant = fvv ? atoi(fvv) : 0;
     const char *fcl = getenv("ADTOMO_FORCE_CLUSTER");
@@ -282,6 +282,7 @@ static adtomo_ctx *default_ctx(int *rc) {
 
 static int check_launch(adtomo_ctx *c, const char *what) {
     c->launches++;
+    if (!strncmp(what, "k_fwd3d", 7)) c->last_fwd_kernel = what;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ADTOMO_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return 0;
@@ -319,16 +320,7 @@ __global__ void k_selftest_sqrt(const long long n, const unsigned long long seed
     }
 }
 
-// debug aid (not part of the ABI): cycle counters of block 0 of the batch forward kernel, see kernels_fwd_v3.cuh
-extern "C" int adtomo_debug_v3_times(long long *out16, int reset) {
-    cudaDeviceSynchronize();
-    if (out16 && cudaMemcpyFromSymbol(out16, v3_diag_times, sizeof(long long) * 16) != cudaSuccess) return -1;
-    if (reset) {
-        long long z[16] = {0};
-        if (cudaMemcpyToSymbol(v3_diag_times, z, sizeof(z)) != cudaSuccess) return -1;
-    }
-    return 0;
-}
+extern "C" const char *adtomo_last_forward_kernel(adtomo_ctx *c) { return c ? c->last_fwd_kernel : ""; }
 
 extern "C" int adtomo_selftest_sqrt(adtomo_ctx *c, long long n, unsigned long long seed, long long *mismatches) {
     if (!c || !mismatches) return fail(ADTOMO_ERR_ARG, "adtomo_selftest_sqrt: null argument");
@@ -482,24 +474,22 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
     pc->m = m; pc->n = n; pc->l = l;
     // 16 warps: two CTAs per SM at 64 registers per thread
     const char *vw = getenv("ADTOMO_V2_WARPS");      // tuning aid
+    const char *vp = getenv("ADTOMO_V2_PLANE_KB");   // testing aid: a small re-skew plane forces W-chunking
+    const size_t plane = vp ? (size_t)atoi(vp) * 1024 : 64 * 1024;
     if (c->v3_mode) {
-        const char *r2 = getenv("ADTOMO_V3_RESKEW");      // 2 (default): cp.async, two stages of 32 KB; 1: register version, one 64 KB plane
-        pc->rsk2 = (r2 ? atoi(r2) : 2) == 2;
-        pc->ok = v3_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, pc->rsk2 ? 32 * 1024 : 64 * 1024, &pc->pct, c->v3_mode == 1);
+        pc->ok = v3_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, plane, &pc->pct, c->v3_mode == 1);
         pc->v3 = pc->ok;
     } else {
-        pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
+        pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, plane);
     }
-    pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS * (pc->v3 && pc->rsk2 ? 2 : 1) : 0;
+    pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
     if (pc->v3) {
         pc->maxPer = v3_max_per_warp(pc->plan);
-        pc->smem_bytes = std::max(pc->smem_bytes, (size_t)2048 * (pc->plan.NT / 32));      // cross-level look-ahead of the sweeps aliases the plane
         if (pc->pct) pc->smem_bytes = std::max(pc->smem_bytes, (size_t)V3_STAGE_BYTES_PER_WARP * (pc->plan.NT / 32));   // cp.async staging aliases the plane
         pc->tabOffset = (int)((pc->smem_bytes + 15) & ~(size_t)15);
         pc->smem_bytes = pc->tabOffset + (sizeof(V3Slot) + sizeof(int)) * (size_t)(pc->plan.NT / 32) * pc->maxPer;
         if (pc->smem_bytes > 100 * 1024) {           // table too large for two CTAs per SM: the round-1 sweep loop
             pc->v3 = false;
-            pc->rsk2 = 0;
             pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
             pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
         }
@@ -570,10 +560,6 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
         LAUNCHED(c, "k2_u0_to_P");
     }
     phase_end(c, pk);
-    if (getenv("ADTOMO_V3_NOSYNC")) {      // timing-only diagnostic, see kernels_fwd_v3.cuh
-        const int one = atoi(getenv("ADTOMO_V3_NOSYNC"));
-        CK(cudaMemcpyToSymbolAsync(v3_diag_nosync, &one, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
-    }
     pk = phase_begin(c, PH_FWD);
 #define V2_LAUNCH(NTMAX_, MINB_)                                                                                       \
     do {                                                                                                               \
@@ -586,25 +572,23 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
         kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol,    \
                                                                                  max_rounds, S, d_rounds, d_errs, where, order, spent); \
     } while (0)
-#define V3_LAUNCH(PCT_, STG_) V3_LAUNCH_NT(512, PCT_, STG_, false)
-#define V3_LAUNCH_NT(NT_, PCT_, STG_, P2_)                                                                             \
+#define V3_LAUNCH(PCT_, STG_)                                                                                          \
     do {                                                                                                               \
-        auto kern = k_fwd3d_v3<NT_, 2, PCT_, STG_, P2_>;                                                                        \
+        auto kern = k_fwd3d_v3<512, 2, PCT_, STG_>;                                                                        \
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                       \
         int occ = 1;                                                                                                   \
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));                           \
         if (occ < 1) occ = 1;                                                                                          \
         if (c->v2_occ > 0 && occ > c->v2_occ) occ = c->v2_occ;                                                         \
         kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, pc->tabOffset, pc->maxPer, bufs, flay, flay + P.M, h, \
-                                                                                 tol, max_rounds, S, d_rounds, d_errs, where, order, spent, pc->rsk2); \
+                                                                                 tol, max_rounds, S, d_rounds, d_errs, where, order, spent); \
     } while (0)
-    if (pc->v3 && P.NT <= 256 && pc->pct == 72) {         // experiment: 8 warps, up to 128 registers
-        if (c->v3_staged == 2) V3_LAUNCH_NT(256, 72, false, true); else V3_LAUNCH_NT(256, 72, false, false);
-    } else if (pc->v3 && P.NT <= 384 && pc->pct == 72) {  // experiment: 12 warps, up to 85 registers
-        if (c->v3_staged == 2) V3_LAUNCH_NT(384, 72, false, true); else V3_LAUNCH_NT(384, 72, false, false);
-    } else if (pc->v3 && P.NT <= 512) {
+    // cp.async look-ahead through shared memory pays when a CTA has its SM to itself (148 sources: 100 vs 111 ms) and
+    // costs with two CTAs per SM (256 sources: 164 vs 140 ms: the L1 data pipe carries every value twice)
+    const bool staged = c->v3_staged == 1 || (c->v3_staged < 0 && S <= c->num_sms);
+    if (pc->v3 && P.NT <= 512) {
         switch (pc->pct) {
-#define V3_CASE(pc_) case pc_: if (c->v3_staged == 1) V3_LAUNCH(pc_, true); else V3_LAUNCH(pc_, false); break;
+#define V3_CASE(pc_) case pc_: if (staged) V3_LAUNCH(pc_, true); else V3_LAUNCH(pc_, false); break;
             V3_PC_MENU(V3_CASE)
 #undef V3_CASE
             default: V3_LAUNCH(0, false); break;
@@ -616,7 +600,6 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     else if (P.NT <= 512) V2_LAUNCH(512, 2);
     else V2_LAUNCH(1024, 1);
 #undef V3_LAUNCH
-#undef V3_LAUNCH_NT
 #undef V2_LAUNCH
     phase_end(c, pk);
     LAUNCHED(c, pc->v3 ? "k_fwd3d_v3" : "k_fwd3d_v2");

@@ -165,12 +165,6 @@ EIK_HD void v3_reskew_index(const Plan2 &P, const int sigma, const int w0, const
 
 #if defined(__CUDACC__)
 
-// TIMING-ONLY diagnostic (wrong results on purpose): no barrier between the levels of a sweep.  Upper bound of what a
-// barrier-free (dataflow) level loop could gain.  Set through adtomo's ADTOMO_V3_NOSYNC=1.
-__device__ int v3_diag_nosync = 0;
-// cycles block 0 spent in the 8 sweeps [0..7], the re-skews [8], everything [9]; rounds [10] (debug aid, adtomo_debug_v3_times)
-__device__ long long v3_diag_times[16];
-
 // Builds the CTA's slot table for a sweep: tab[w * maxPer + j] = j-th slot of warp w (ranks w, w + nw, ...),
 // tabS[same] = its first live level.
 template <int SA, int SW, int SC>
@@ -245,87 +239,9 @@ __device__ __forceinline__ void v3_reskew(const Plan2 &P, const double *src, dou
     }
 }
 
-// ---- re-skew with cp.async, two plane stages ----
-// The register version above reads a chunk (global -> registers -> plane), waits, writes it (plane -> registers ->
-// global), waits: per chunk the DRAM latency of the reads is exposed twice over (8 elements in flight per thread) and
-// nothing overlaps the writes; it took 18 % of the kernel.  Here a chunk travels global -> plane with cp.async (all of a
-// thread's elements in flight, no registers) into one of TWO plane stages, and the reads of chunk c+1 are in flight while
-// chunk c is written out.  Chunks run across slab boundaries (one flat sequence of (slab, W-chunk) pairs).
-__device__ __forceinline__ void v3_cp8a(const unsigned s, const void *g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(g) : "memory");
-}
-
-// element (v, C) of a chunk in layout sigma -> plane slot / slab offset (fast map when the chunk is at least dC rows)
-__device__ __forceinline__ void v3_reskew_any_index(const Plan2 &P, const int sigma, const int w0, const int wc, const int v,
-                                                    const int C, int &pl, int &go) {
-    if (wc >= P.dC) v3_reskew_index(P, sigma, w0, wc, v, C, pl, go);
-    else v2_reskew_index(P, sigma, w0, wc, v, C, pl, go);
-}
-
-__device__ __forceinline__ void v3_reskew_issue(const Plan2 &P, const double *src, const int sigmaFrom, double *stage,
-                                                const int chunk, const int cps) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int A = chunk / cps, w0 = (chunk - A * cps) * P.WCH;
-    const int wc = (P.dW - w0 < P.WCH) ? P.dW - w0 : P.WCH;
-    const double *s = src + (long long)(A + 1) * P.RS * P.PC;
-    const unsigned sb = (unsigned)__cvta_generic_to_shared(stage);
-    for (int C = lane; C < P.dC; C += 32)
-        for (int v = warp; v < wc; v += nw) {
-            int pl, go;
-            v3_reskew_any_index(P, sigmaFrom, w0, wc, v, C, pl, go);
-            v3_cp8a(sb + pl * 8, s + go);
-        }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-__device__ __forceinline__ void v3_reskew_drain(const Plan2 &P, double *dst, const int sigmaTo, const double *stage,
-                                                const int chunk, const int cps) {
-    constexpr int U = 4;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int A = chunk / cps, w0 = (chunk - A * cps) * P.WCH;
-    const int wc = (P.dW - w0 < P.WCH) ? P.dW - w0 : P.WCH;
-    double *d = dst + (long long)(A + 1) * P.RS * P.PC;
-    for (int C = lane; C < P.dC; C += 32)
-        for (int v0 = warp; v0 < wc; v0 += U * nw) {
-            int gos[U];
-            double x[U];
-#pragma unroll
-            for (int j = 0; j < U; j++) {
-                int pl = 0;
-                gos[j] = 0;
-                x[j] = 0.0;
-                if (v0 + j * nw < wc) {
-                    v3_reskew_any_index(P, sigmaTo, w0, wc, v0 + j * nw, C, pl, gos[j]);
-                    x[j] = stage[pl];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < U; j++)
-                if (v0 + j * nw < wc) d[gos[j]] = x[j];
-        }
-}
-
-// whole field, slabs [0, dA): plane holds two stages of WCH x PS doubles
-__device__ __forceinline__ void v3_reskew_async(const Plan2 &P, const double *src, double *dst, const int sigmaFrom, double *plane) {
-    const int cps = (P.dW + P.WCH - 1) / P.WCH, n = P.dA * cps;
-    const int stageLen = P.WCH * P.PS;
-    v3_reskew_issue(P, src, sigmaFrom, plane, 0, cps);
-    for (int c = 0; c < n; c++) {
-        if (c + 1 < n) {
-            v3_reskew_issue(P, src, sigmaFrom, plane + ((c + 1) & 1) * stageLen, c + 1, cps);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();                       // every thread's copies of chunk c have landed
-        v3_reskew_drain(P, dst, -sigmaFrom, plane + (c & 1) * stageLen, c, cps);
-        __syncthreads();                       // stage c & 1 may be refilled (by chunk c + 2, issued in the next turn)
-    }
-}
-
-template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT, bool PIPE2 = false>
-__device__ __forceinline__ void v3_sweep(const Plan2 &P, V3Slot *tab, int *tabS, const int maxPer, double *stage, const double *rd,
-                                         double *wr, const double *__restrict__ fl, const double *cmp, const double h, double &err) {
+template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT>
+__device__ __forceinline__ void v3_sweep(const Plan2 &P, V3Slot *tab, int *tabS, const int maxPer, const double *rd, double *wr,
+                                         const double *__restrict__ fl, const double *cmp, const double h, double &err) {
     const int PC = PCT ? PCT : P.PC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const V2Lane L = v2_lane_setup<SA, SW, SC>(P, lane);      // P.PC == PC (the plan was built for this pitch)
@@ -334,9 +250,6 @@ __device__ __forceinline__ void v3_sweep(const Plan2 &P, V3Slot *tab, int *tabS,
     const int cnt = warp < nslots ? (nslots - warp + nw - 1) / nw : 0;
     const int dur = v3_duration(P);
     const long long sAb = (long long)P.RS * PC * 8;
-    const int diag = v3_diag_nosync;
-    const int nosync = v3_diag_nosync & 1;
-    const bool xlevel = !(v3_diag_nosync & 2);       // A/B knob: 2 = no loads across the level barrier
     __syncthreads();     // the previous sweep (its field writes, its use of the table) is complete
     v3_build_table<SA, SW, SC>(P, PC, tab, tabS, maxPer);
     __syncthreads();
@@ -346,126 +259,45 @@ __device__ __forceinline__ void v3_sweep(const Plan2 &P, V3Slot *tab, int *tabS,
     int sTail = cnt > 0 ? mineS[0] : 0x7fffffff;     // first level of the next slot to enter the window
     int sHead = sTail;                                // first level of the oldest slot in the window
     int lamOff = L.offc, lamWb = L.wqc + V3_BIAS;
-    // window of level 0
-    while (sTail <= 0) {
-        tail++;
-        sTail = tail < cnt ? mineS[tail] : 0x7fffffff;
-    }
-#define V3_NODE(off_, act_)                                                                      \
+    for (int lam = 0; lam < P.nlev; lam++, lamOff += SW * PC, lamWb++) {
+        while (sTail <= lam) {
+            tail++;
+            sTail = tail < cnt ? mineS[tail] : 0x7fffffff;
+        }
+        while (head < tail && sHead + dur < lam) {
+            head++;
+            sHead = head < cnt ? mineS[head] : 0x7fffffff;
+        }
+        // The loads of the warp's next slot are issued before the current slot's arithmetic (software pipelining by
+        // hand).  Measured and rejected (profiles/r02_v3_phase_cycles.json): a second register set (spills at 64
+        // registers; CTAs of 384 / 256 threads with 80 / 114 registers lose more to the missing warps), carrying the
+        // look-ahead across the level barrier, L2 prefetch of the next level's rows.
+#define V3_LOAD(V_)                                                                              \
     do {                                                                                         \
         const int2 d2__ = *dp++;                                                                 \
         V3Slot d__;                                                                              \
         d__.base = d2__.x; d__.meta = d2__.y;                                                    \
-        v3_node(P, d__, lamOff, lamWb, lmask, off_, act_);                                       \
-    } while (0)
-#define V3_LOAD(V_)                                                                              \
-    do {                                                                                         \
         int off__; bool act__;                                                                   \
-        V3_NODE(off__, act__);                                                                   \
-        if (diag & 8) {  /* timing only: no loads */                                             \
-            V_.off = act__ ? off__ : -1; V_.own = 1000.0; V_.fv = 0.2; V_.dA = off__ * 1e-3; V_.dW = V_.dA + 0.1; V_.dC = V_.dA + 0.15; \
-            V_.uA = V_.dA + 0.01; V_.uW = V_.dA + 0.12; V_.uC = V_.dA + 0.2; V_.ref = 0.0;     \
-        } else                                                                                   \
+        v3_node(P, d__, lamOff, lamWb, lmask, off__, act__);                                     \
         v3_load<SA, SW, SC, OOP, CMP, PCT>(P, sAb, off__, act__, rd, wr, fl, cmp, V_);           \
     } while (0)
-#define V3_SOLVE(Q_)                                                                             \
-    do {                                                                                         \
-        if (diag & 4) {  /* timing only: trivial arithmetic */                                   \
-            if (Q_.off >= 0) { const double r__ = Q_.a1 + Q_.fv * h; if (r__ < Q_.own && !(diag & 16)) wr[Q_.off] = r__; } \
-        } else if (diag & 16) { /* timing only: no stores */                                     \
-            double dummy__[1]; V2Prep q__ = Q_; q__.off = Q_.off >= 0 ? 0 : -1; v2_solve<OOP, CMP>(q__, dummy__ , h, err); err += dummy__[0]; \
-        } else                                                                                   \
-        v2_solve<OOP, CMP>(Q_, wr, h, err);                                                      \
-    } while (0)
-    // cross-level look-ahead: six values per lane in shared memory (the re-skew plane is idle during a sweep), lane-private
-    double *sp = stage + warp * 256 + lane;           // value k: sp[k * 32]
-    const unsigned sb = (unsigned)__cvta_generic_to_shared(sp);
-    bool pre = false, preAct = false;
-    int preOff = 0;
-    for (int lam = 0; lam < P.nlev; lam++) {
-        // The loads of the warp's next slot are issued before the current slot's arithmetic (software pipelining by
-        // hand; a two-register-set version without copies on the back edge spills at 64 registers).  The pipeline is
-        // carried ACROSS the level barrier for the values that do not depend on the level that is ending: during its
-        // last slot of a level the warp already loads own / f / downwind values of its first slot of the next level
-        // (the first touch of those lines -- the DRAM latency -- was exposed once per level and warp: about half of
-        // the kernel time by a fit over CTA sizes); only the three upwind values are loaded after the barrier.  The
-        // look-ahead travels through shared memory with cp.async: in registers the compiler spills it to local
-        // memory right behind the loads, i.e. waits for them before the last solve.
         int left = tail - head;
-        bool advanced = false;
-        if (PIPE2) {
-            if (left > 0) {
-                const int2 *dp = mine + head;
-                V2Vals V0, V1;
-                V2Prep Q;
-                V3_LOAD(V0);
-                if (left > 1) V3_LOAD(V1);
-#pragma unroll 1
-                for (;;) {
-                    v2_prep(V0, Q);
-                    if (left > 2) V3_LOAD(V0);
-                    V3_SOLVE(Q);
-                    if (--left <= 0) break;
-                    v2_prep(V1, Q);
-                    if (left > 2) V3_LOAD(V1);
-                    V3_SOLVE(Q);
-                    if (--left <= 0) break;
-                }
-            }
-        } else if (left > 0) {
+        if (left > 0) {
             const int2 *dp = mine + head;
             V2Vals V;
-            if (pre) {
-                dp++;
-                v3_load_up<SA, SW, SC, OOP, PCT>(P, sAb, preOff, rd, wr, V);
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                V.own = sp[0 * 32]; V.fv = sp[1 * 32]; V.dW = sp[2 * 32]; V.dC = sp[3 * 32]; V.dA = sp[4 * 32];
-                V.ref = CMP ? sp[5 * 32] : 0.0;
-                V.off = preAct ? preOff : -1;
-            } else {
-                V3_LOAD(V);
-            }
-            pre = false;
+            V3_LOAD(V);
 #pragma unroll 1
             for (;;) {
                 V2Prep Q;
                 v2_prep(V, Q);                     // consumes V: its registers take the next slot's loads
-                if (--left > 0) {
-                    V3_LOAD(V);
-                } else if (xlevel) {
-                    // last slot of the level: next level's window, and the old values of its first slot
-                    lamOff += SW * PC; lamWb++;
-                    while (sTail <= lam + 1) { tail++; sTail = tail < cnt ? mineS[tail] : 0x7fffffff; }
-                    while (head < tail && sHead + dur < lam + 1) { head++; sHead = head < cnt ? mineS[head] : 0x7fffffff; }
-                    advanced = true;
-                    if (tail > head && lam + 1 < P.nlev) {
-                        dp = mine + head;
-                        V3_NODE(preOff, preAct);
-                        const double *p__ = rd + preOff;
-                        v3_cp8a(sb + 0 * 256, p__);
-                        v3_cp8a(sb + 1 * 256, fl + preOff);
-                        v3_cp8a(sb + 2 * 256, p__ + SW * PC);
-                        v3_cp8a(sb + 3 * 256, p__ + (SW * PC + SC));
-                        v3_cp8a(sb + 4 * 256, reinterpret_cast<const char *>(p__) + SA * sAb);
-                        if (CMP) v3_cp8a(sb + 5 * 256, cmp + preOff);
-                        asm volatile("cp.async.commit_group;" ::: "memory");
-                        pre = true;
-                    }
-                }
-                V3_SOLVE(Q);
+                if (--left > 0) V3_LOAD(V);
+                v2_solve<OOP, CMP>(Q, wr, h, err);
                 if (left <= 0) break;
             }
         }
-        if (!advanced) {
-            lamOff += SW * PC; lamWb++;
-            while (sTail <= lam + 1) { tail++; sTail = tail < cnt ? mineS[tail] : 0x7fffffff; }
-            while (head < tail && sHead + dur < lam + 1) { head++; sHead = head < cnt ? mineS[head] : 0x7fffffff; }
-        }
-        if (!nosync) __syncthreads();
-    }
 #undef V3_LOAD
-#undef V3_SOLVE
-#undef V3_NODE
+        __syncthreads();
+    }
 }
 
 // ---- staged variant: the eight values of a node travel global -> shared memory with cp.async, two warp slots ahead ----
@@ -577,13 +409,13 @@ __device__ __forceinline__ void v3_sweep_staged(const Plan2 &P, V3Slot *tab, int
 // Same contract as k_fwd3d_v2 (buffers, order, rounds, errs, where, spent); the field and slowness buffers have
 // v3_slack() loadable doubles on both sides.  Dynamic shared memory: the re-skew plane (WCH x PS doubles) followed by
 // the slot table (nw x maxPer int2, then nw x maxPer int).
-template <int NTMAX, int MINB, int PCT, bool STG, bool PIPE2 = false>
+template <int NTMAX, int MINB, int PCT, bool STG>
 __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const int tabOffset, const int maxPer, double *bufs,
                                                           const double *__restrict__ fP, const double *__restrict__ fM,
                                                           const double h, const double tol, const int max_rounds,
                                                           const int S, int *__restrict__ rounds, double *__restrict__ errs,
                                                           int *__restrict__ where, const int *__restrict__ order,
-                                                          int *__restrict__ spent, const int rsk2) {
+                                                          int *__restrict__ spent) {
     extern __shared__ double plane[];
     __shared__ double red[32];
     V3Slot *tab = reinterpret_cast<V3Slot *>(reinterpret_cast<char *>(plane) + tabOffset);
@@ -601,29 +433,23 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const i
             double *w = Ba;
             for (int sw = 0; sw < 8; sw++) {
                 const int sigma = P.sg[sw][1] * P.sg[sw][2];
-                long long tq0 = clock64();
                 if (sw > 0 && sigma != state) {
                     double *dst = state > 0 ? Bz : Ba;
                     __syncthreads();
-                    if (rsk2) v3_reskew_async(P, w, dst, state, plane);
-                    else v3_reskew(P, w, dst, state, plane, 0, P.dA);
+                    v3_reskew(P, w, dst, state, plane, 0, P.dA);
                     w = dst;
                     state = sigma;
-                    __syncthreads();
-                    if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t = clock64(); v3_diag_times[8] += t - tq0; tq0 = t; }
                 }
 #define V3_CALL(a_, w_, c_, oop_, cmp_)                                                                                  \
     do {                                                                                                                 \
         if constexpr (STG && PCT != 0)                                                                                   \
             v3_sweep_staged<a_, w_, c_, oop_, cmp_, PCT>(P, tab, tabS, maxPer, plane, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
         else                                                                                                             \
-            v3_sweep<a_, w_, c_, oop_, cmp_, PCT, PIPE2>(P, tab, tabS, maxPer, plane, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
+            v3_sweep<a_, w_, c_, oop_, cmp_, PCT>(P, tab, tabS, maxPer, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
     } while (0)
                 V2_DISPATCH(P, sw, V3_CALL);
 #undef V3_CALL
-                if (blockIdx.x == 0 && threadIdx.x == 0) v3_diag_times[sw] += clock64() - tq0;
             }
-            if (blockIdx.x == 0 && threadIdx.x == 0) v3_diag_times[10] += 1;
             const double e = v2_block_max(err, red);
             if (threadIdx.x == 0 && errs) errs[(long long)order[src] * max_rounds + r] = e;
             r++;

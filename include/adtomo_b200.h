@@ -62,6 +62,9 @@ double adtomo_last_kernel_ms(adtomo_ctx *ctx);
 double adtomo_last_phase_ms(adtomo_ctx *ctx, int phase);
 /* Number of kernels this library has launched on the context since creation. */
 long long adtomo_launch_count(adtomo_ctx *ctx);
+/* Name of the 3D forward sweep kernel the last 3D call ran on ("k_fwd3d_v3", "k_fwd3d_team", "k_fwd3d_v1", ...):
+   the tests use it to prove which kernel family they compared with the oracle. */
+const char *adtomo_last_forward_kernel(adtomo_ctx *ctx);
 /* Self-test: the library's call-free fp64 square root (csrc/eik_core.h) against the CUDA math library's
    correctly rounded sqrt on n pseudo-random and special arguments; *mismatches must come back 0. */
 int adtomo_selftest_sqrt(adtomo_ctx *ctx, long long n, unsigned long long seed, long long *mismatches);
