@@ -68,6 +68,10 @@ def load_library():
     L.adtomo_last_phase_ms.argtypes = [_vp, c_int]
     L.adtomo_launch_count.restype = ctypes.c_longlong
     L.adtomo_launch_count.argtypes = [_vp]
+    L.adtomo_phase_accumulate.restype = c_int
+    L.adtomo_phase_accumulate.argtypes = [_vp, c_int]
+    L.adtomo_set_batch_id.restype = c_int
+    L.adtomo_set_batch_id.argtypes = [_vp, ctypes.c_longlong]
     L.adtomo_last_forward_kernel.restype = ctypes.c_char_p
     L.adtomo_last_forward_kernel.argtypes = [_vp]
     L.adtomo_selftest_sqrt.restype = c_int
@@ -156,6 +160,14 @@ class Context:
     @property
     def stream(self):
         return int(self._lib.adtomo_stream(self.handle))
+
+    def phase_accumulate(self, on):
+        """Keep the per-kernel event pairs of every following call (phase_ms then sums over all of them)."""
+        check(self._lib.adtomo_phase_accumulate(self.handle, 1 if on else 0), "adtomo_phase_accumulate")
+
+    def set_batch_id(self, batch_id):
+        """Names the source batch of the following batched calls (placement memo of the batch kernel)."""
+        check(self._lib.adtomo_set_batch_id(self.handle, int(batch_id)), "adtomo_set_batch_id")
 
     def last_kernel(self):
         """Name of the 3D forward sweep kernel of the last call."""

@@ -55,6 +55,7 @@ struct adtomo_ctx {
     // per-phase device timing of the last call: pairs of events around the kernels of each phase
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     std::vector<std::pair<int, int>> ev_used;   // (phase, pool index)
+    int phase_acc = 0;                          // adtomo_phase_accumulate: keep the event pairs of earlier calls
     std::vector<struct PlanCache *> plans;      // level-major layout plans, one per grid shape
     int fwd_variant = 0;                        // tuning aid: ADTOMO_FWD_VARIANT selects <threads, nodes per lane>
     NcclApi::Comm nccl_comm = nullptr;          // set by adtomo_nccl_init
@@ -65,7 +66,8 @@ struct adtomo_ctx {
     int force_v2 = 0;                           // debugging aid: ADTOMO_FORCE_V2=1 selects the skewed-pencil kernel for any batch
     std::map<std::pair<long long, int>, int> chunk_cache;   // sources per chunk of the fused step, per (grid, batch)
     int v2_pairing = 1;                         // tuning aid: ADTOMO_V2_PAIRING=0 keeps sources in caller order
-    std::map<std::tuple<const void *, int, const void *>, int *> v2_spent;   // rounds per source of earlier calls, per batch
+    std::map<std::tuple<const void *, int, long long>, int *> v2_spent;   // rounds per source of earlier calls, per batch (plan, S, batch id)
+    long long batch_id = 0;                     // adtomo_set_batch_id: names the source batch of the following calls
     const char *last_fwd_kernel = "";           // name of the last 3D forward sweep kernel launched (adtomo_last_forward_kernel)
     int v3_mode = 1;                            // ADTOMO_V3: 1 (default) batch sweeps of kernels_fwd_v3.cuh with menu pitch, 2 same with run-time pitch, 0 the round-1 sweep loop (cross-check)
     int v3_staged = -1;                         // ADTOMO_V3_STAGED: cp.async look-ahead through shared memory: -1 automatic (one CTA per SM), 0 never, 1 always
@@ -115,7 +117,7 @@ struct PlanCache {
 
 enum { PH_FWD = 0, PH_MISFIT = 1, PH_ADJ_SETUP = 2, PH_ADJ_SWEEP = 3, PH_ADJ_FINISH = 4, PH_CONVERT = 5, PH_COUNT = 6 };
 
-static void phase_reset(adtomo_ctx *c) { c->ev_used.clear(); }
+static void phase_reset(adtomo_ctx *c) { if (!c->phase_acc) c->ev_used.clear(); }
 static int phase_begin(adtomo_ctx *c, int phase) {
     size_t k = c->ev_used.size();
     if (k >= c->ev_pool.size()) {
@@ -251,7 +253,9 @@ extern "C" int adtomo_synchronize(adtomo_ctx *c) {
 extern "C" unsigned long long adtomo_stream(adtomo_ctx *c) { return c ? (unsigned long long)(uintptr_t)c->stream : 0ULL; }
 extern "C" long long adtomo_launch_count(adtomo_ctx *c) { return c ? c->launches : 0; }
 extern "C" double adtomo_last_kernel_ms(adtomo_ctx *c) {
-    if (!c || !c->timed) return -1.0;
+    if (!c) return -1.0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->timed) return -1.0;
     cudaSetDevice(c->device);
     if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
     float ms = 0.f;
@@ -259,8 +263,17 @@ extern "C" double adtomo_last_kernel_ms(adtomo_ctx *c) {
     return (double)ms;
 }
 
+extern "C" int adtomo_phase_accumulate(adtomo_ctx *c, int on) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "adtomo_phase_accumulate: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->ev_used.clear();
+    c->phase_acc = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" double adtomo_last_phase_ms(adtomo_ctx *c, int phase) {
     if (!c) return -1.0;
+    std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     double tot = 0.0;
@@ -321,6 +334,13 @@ __global__ void k_selftest_sqrt(const long long n, const unsigned long long seed
 }
 
 extern "C" const char *adtomo_last_forward_kernel(adtomo_ctx *c) { return c ? c->last_fwd_kernel : ""; }
+
+extern "C" int adtomo_set_batch_id(adtomo_ctx *c, long long id) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "adtomo_set_batch_id: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->batch_id = id;
+    return 0;
+}
 
 extern "C" int adtomo_selftest_sqrt(adtomo_ctx *c, long long n, unsigned long long seed, long long *mismatches) {
     if (!c || !mismatches) return fail(ADTOMO_ERR_ARG, "adtomo_selftest_sqrt: null argument");
@@ -524,7 +544,7 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     order = where + S;
     // rounds each source of THIS batch needed last time (batch = plan, size, caller's rounds array)
     {
-        const auto key = std::make_tuple((const void *)pc, S, (const void *)d_rounds);
+        const auto key = std::make_tuple((const void *)pc, S, c->batch_id);
         auto it = c->v2_spent.find(key);
         if (it == c->v2_spent.end()) {
             if (c->v2_spent.size() > 64) {          // bounded: forget everything

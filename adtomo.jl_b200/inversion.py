@@ -49,8 +49,12 @@ class InversionProblem:
     [grad | misfit] buffer over ranks with ONE collective (replaces mpi_sum + the backward of
     mpi_bcast)."""
 
+    _next_batch_id = 1
+
     def __init__(self, ctx, dims, h, sta_xyz, eve_xyz, uobs, qua, vel0, tol=1e-3, u0_fill=1000.0, max_rounds=0):
         self.ctx = ctx
+        self.batch_id = InversionProblem._next_batch_id          # names this source set for the batch kernel's placement memo
+        InversionProblem._next_batch_id += 1
         self.dims = tuple(int(d) for d in dims)
         self.N = self.dims[0] * self.dims[1] * self.dims[2]
         self.h = float(h)
@@ -69,6 +73,7 @@ class InversionProblem:
         """f: (m,n,l) host slowness.  Returns (misfit, grad_f (m,n,l) or None, rc)."""
         f = capi.f64(f).reshape(self.dims)
         packed = np.empty(self.N + 1, dtype=np.float64) if want_grad else None
+        self.ctx.set_batch_id(self.batch_id)
         mis, rc = self.ctx.misfit_grad(packed, f, self.h, self.dims, self.tol, self.S, self.src_ptr, self.src_idx,
                                        self.src_val, self.u0_fill, self.E, self.rcv, self.uobs, self.qua,
                                        max_rounds=self.max_rounds, rounds=self.rounds, loc=capi.HOST)

@@ -60,8 +60,17 @@ double adtomo_last_kernel_ms(adtomo_ctx *ctx);
  * 1 = receiver sampling/misfit, 2 = adjoint setup, 3 = adjoint wavefront kernel, 4 = gradient finish,
  * 5 = layout conversions around the forward kernel. */
 double adtomo_last_phase_ms(adtomo_ctx *ctx, int phase);
+/* on != 0: from now on the event pairs of every call are kept and adtomo_last_phase_ms sums over all calls since
+   (a benchmark reads the per-kernel device times of its whole timed region AFTER the region, without synchronising
+   inside it); on == 0: back to "last call only".  Either way the accumulated pairs are dropped. */
+int adtomo_phase_accumulate(adtomo_ctx *ctx, int on);
 /* Number of kernels this library has launched on the context since creation. */
 long long adtomo_launch_count(adtomo_ctx *ctx);
+/* Names the batch of sources the following batched 3D calls work on (default 0).  The batch kernel remembers, per
+   (grid, number of sources, batch id), how many rounds every source needed in the previous call and places long and
+   short sources together on an SM; a driver that alternates between several source sets (e.g. the P and the S stations)
+   gives each its own id.  Purely a performance hint: results do not depend on it. */
+int adtomo_set_batch_id(adtomo_ctx *ctx, long long id);
 /* Name of the 3D forward sweep kernel the last 3D call ran on ("k_fwd3d_v3", "k_fwd3d_team", "k_fwd3d_v1", ...):
    the tests use it to prove which kernel family they compared with the oracle. */
 const char *adtomo_last_forward_kernel(adtomo_ctx *ctx);
