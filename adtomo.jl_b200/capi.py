@@ -8,7 +8,8 @@ import numpy as np
 
 HOST, DEVICE = 0, 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadtomo_b200.so")
+# ADTOMO_LIB: A/B runs of differently built libraries (benchmarks only); the default is the in-tree build
+LIB_PATH = os.environ.get("ADTOMO_LIB") or os.path.join(_HERE, "libadtomo_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "adtomo_b200.h")
 
 _dp = ctypes.POINTER(ctypes.c_double)

@@ -15,6 +15,7 @@
 #include "../../include/adtomo_b200.h"
 #include "kernels_v0.cuh"
 #include "kernels_adj_topo.cuh"
+#include "kernels_adj_sparse.cuh"
 #include "kernels_fwd_v1.cuh"
 #include "kernels_fwd_v2.cuh"
 #include "kernels_fwd_v3.cuh"
@@ -95,6 +96,7 @@ struct adtomo_ctx {
     int team_nt = 512;                          // 16 warps, <= 64 registers: two CTAs per SM
     int coop_launch = 1;                        // cudaDevAttrCooperativeLaunch; without it the team kernels are never selected
     int adj_team = 0;                           // tuning aid: ADTOMO_ADJ_TEAM = CTAs per source of the adjoint wavefront (0: automatic, 1: single-CTA kernel)
+    int adj_sparse = -1;                        // ADTOMO_ADJ_SPARSE: active-set adjoint (kernels_adj_sparse.cuh): -1 automatic (batches whose right-hand side is known to be sparse: the fused step), 0 never, 1 every batch
 };
 
 struct Plan2Cache {
@@ -214,6 +216,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     }
     const char *atm = getenv("ADTOMO_ADJ_TEAM");
     c->adj_team = atm ? atoi(atm) : 0;
+    const char *asp = getenv("ADTOMO_ADJ_SPARSE");
+    c->adj_sparse = asp ? atoi(asp) : -1;
     const char *ts0 = getenv("ADTOMO_TEAM_SERIAL0");      // testing aid: start the mailbox tag serial near its wrap
     c->team_serial_start = ts0 ? (unsigned)strtoul(ts0, nullptr, 10) : 0u;
     const char *tmr = getenv("ADTOMO_TEAM_R");
@@ -814,9 +818,61 @@ static int fwd3d_device(adtomo_ctx *c, double *dU, const double *df, const Dims3
     return 0;
 }
 
+// Active-set adjoint for batches (kernels_adj_sparse.cuh): one CTA per source, only the ancestors of the nodes with a
+// non-zero right-hand side are visited by the wavefronts.
+static int adj3d_sparse(adtomo_ctx *c, const double *dU, const double *dU0, const double *dG, const double *df,
+                        double *dGU0, double *dGF, double *dGFsum, const Dims3 &d, double h, int S, int *d_status) {
+    double2 *UX, *GD;
+    unsigned *W;
+    int *Q1, *Q2, *tails;
+    const size_t total = (size_t)S * d.N;
+    WS(c, "adj_ux", double2, total, UX);
+    WS(c, "adj_gd", double2, total, GD);
+    WS(c, "adj_w", unsigned, total, W);
+    WS(c, "adj_queue", int, total, Q1);
+    WS(c, "adj_queue2", int, total, Q2);
+    WS(c, "adj_counters", int, 8 * (size_t)S, tails);
+    CK(cudaMemsetAsync(tails, 0, sizeof(int) * S, c->stream));
+    const dim3 eg(std::min(elem_grid(c, d.N), std::max(128, 16 * c->num_sms / S)), S);
+    int pk = phase_begin(c, PH_ADJ_SETUP);
+    k_adj3d_setup3<<<eg, 256, 0, c->stream>>>(dU, dU0, dG, UX, GD, dGU0, W, Q1, tails, d, S);
+    phase_end(c, pk);
+    LAUNCHED(c, "k_adj3d_setup3");
+    if (!dGF && !dGFsum) return 0;
+    static const int nt_env = getenv("ADTOMO_ADJ_NT") ? atoi(getenv("ADTOMO_ADJ_NT")) : 0;
+    const int nt = nt_env ? nt_env : 1024;
+    pk = phase_begin(c, PH_ADJ_SWEEP);
+#define ASP_LAUNCH(NT_)                                                                                               \
+    do {                                                                                                              \
+        int occ = 1;                                                                                                  \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_sparse<NT_>, NT_, 0));                         \
+        if (occ < 1) occ = 1;                                                                                         \
+        k_adj3d_sparse<NT_><<<std::min(S, c->num_sms * occ), NT_, 0, c->stream>>>(UX, GD, W, Q1, Q2, tails, d, S, d_status); \
+    } while (0)
+    if (nt <= 256) ASP_LAUNCH(256);
+    else if (nt <= 512) ASP_LAUNCH(512);
+    else ASP_LAUNCH(1024);
+#undef ASP_LAUNCH
+    phase_end(c, pk);
+    LAUNCHED(c, "k_adj3d_sparse");
+    pk = phase_begin(c, PH_ADJ_FINISH);
+    k_adj3d_finish2<<<elem_grid(c, d.N), 256, 0, c->stream>>>(UX, df, dGF, dGFsum, d.N, S, h);
+    phase_end(c, pk);
+    LAUNCHED(c, "k_adj3d_finish2");
+    return 0;
+}
+
+// sparse_rhs: the caller knows that grad_u is non-zero at few nodes only (the fused step: receiver cell corners)
 static int adj3d_device(adtomo_ctx *c, const double *dU, const double *dU0, const double *dG, const double *df,
                         double *dGU0, double *dGF, double *dGFsum, const Dims3 &d, double h, int S,
-                        int *d_status) {
+                        int *d_status, bool sparse_rhs = false) {
+    if (c->adj_sparse == 1 || (c->adj_sparse < 0 && sparse_rhs)) {
+        // few sources: the team wavefront spreads one source over many SMs and wins although it visits every node
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adj3d_topo_team<512>, 512, 0) != cudaSuccess) { cudaGetLastError(); occ = 0; }
+        const bool team = c->coop_launch && !(c->team_mode == 0 && c->adj_team == 0) && c->adj_team != 1 && occ * c->num_sms / S >= 8;
+        if (!team || c->adj_sparse == 1) return adj3d_sparse(c, dU, dU0, dG, df, dGU0, dGF, dGFsum, d, h, S, d_status);
+    }
     double2 *UX, *GD;
     unsigned char *code, *cnt;
     unsigned short *CM;
@@ -1318,7 +1374,7 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
         LAUNCHED(c, "k_misfit");
         if (grad_f) {
             double *target = (Sc < S) ? dSumChunk : dSum;
-            if ((rc = adj3d_device(c, dU, dU0, dG, df, nullptr, nullptr, target, d, h, sc, dSt + s0))) return rc;
+            if ((rc = adj3d_device(c, dU, dU0, dG, df, nullptr, nullptr, target, d, h, sc, dSt + s0, true))) return rc;
             if (Sc < S) {
                 k_axpy<<<elem_grid(c, d.N), 256, 0, c->stream>>>(dSum, dSumChunk, d.N);
                 LAUNCHED(c, "k_axpy");

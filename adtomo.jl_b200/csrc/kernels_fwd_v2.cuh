@@ -41,8 +41,18 @@
 
 namespace adtomo {
 
-constexpr int V2_LA = 4;   // rows of the lane patch
-constexpr int V2_LC = 8;   // columns of the lane patch
+// Lane patch of a warp slot: LA rows x LC columns of pencils (LA * LC = 32).  Build-time knobs for A/B runs
+// (-DADTOMO_V2_LA=2 -DADTOMO_V2_LC=16): wider patches halve the L1 wavefronts per load (rows of 128 instead of 64 bytes)
+// and keep a slot live for LA + LC - 2 more levels than the pencils are long.
+#ifndef ADTOMO_V2_LA
+#define ADTOMO_V2_LA 4
+#endif
+#ifndef ADTOMO_V2_LC
+#define ADTOMO_V2_LC 8
+#endif
+constexpr int V2_LA = ADTOMO_V2_LA;   // rows of the lane patch
+constexpr int V2_LC = ADTOMO_V2_LC;   // columns of the lane patch
+static_assert(V2_LA * V2_LC == 32, "a warp slot is one node per lane");
 
 struct Plan2 {
     int ext[3];          // m, n, l

@@ -32,7 +32,13 @@ namespace adtomo {
 
 // Row pitches the batch kernel is compiled for (doubles; multiples of 8 so that a lane patch row is one
 // 64-byte run).  dC + 1 <= PC.  0 = run-time pitch (any grid).
+#if ADTOMO_V2_LC == 16
+#define V3_PC_MENU(X) X(48) X(80) X(112) X(144) X(272)
+#elif ADTOMO_V2_LC == 32
+#define V3_PC_MENU(X) X(64) X(96) X(160) X(288)
+#else
 #define V3_PC_MENU(X) X(40) X(72) X(104) X(136) X(264)
+#endif
 
 inline int v3_menu_pitch(int dC) {
 #define V3_PICK(pc_) if (dC + 1 <= pc_) return pc_;
