@@ -99,6 +99,17 @@ def load_library():
     L.adtomo_eikonal3d_misfit_grad.restype = c_int
     L.adtomo_eikonal3d_misfit_grad.argtypes = [_vp, _vp, _vp, _vp, c_double, c_int, c_int, c_int, c_double, c_int,
                                                c_int, _vp, _vp, _vp, c_double, c_int, _vp, _vp, _vp, _vp, c_int]
+    L.adtomo_model_begin.restype = c_int
+    L.adtomo_model_begin.argtypes = [_vp, _vp, _vp, c_int, c_int, c_int, c_int]
+    L.adtomo_model_add_phase.restype = c_int
+    L.adtomo_model_add_phase.argtypes = [_vp, c_double, c_double, c_double, c_int, c_int, _vp, _vp, _vp, c_double, c_int,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, c_int, c_int]
+    L.adtomo_model_finish.restype = c_int
+    L.adtomo_model_finish.argtypes = [_vp, c_double, c_int, c_int, c_int, c_int, _vp, _vp, c_int]
+    L.adtomo_model_loss_grad.restype = c_int
+    L.adtomo_model_loss_grad.argtypes = [_vp, _vp, _vp, _vp, _vp, c_double, c_int, c_int, c_int, c_double, c_int, c_int,
+                                         c_int, c_double, c_int, c_int, _vp, _vp, _vp, c_double, c_int, _vp, _vp, _vp,
+                                         _vp, c_int]
     L.adtomo_nccl_unique_id.restype = c_int
     L.adtomo_nccl_unique_id.argtypes = [ctypes.c_char_p]
     L.adtomo_nccl_init.restype = c_int
@@ -249,3 +260,39 @@ class Context:
                                                           int(E), ptr(rcv_xyz), ptr(uobs), ptr(qua), ptr(rounds), loc),
                    "adtomo_eikonal3d_misfit_grad")
         return mis.value, rc
+
+    # ---- model parametrisation + chain rule + regulariser on the device --------------------------
+    def model_begin(self, x, vel0, dims, loc=HOST):
+        m, n, l = dims
+        check(self._lib.adtomo_model_begin(self.handle, ptr(x), ptr(vel0), m, n, l, loc), "adtomo_model_begin")
+
+    def model_add_phase(self, scale, h, tol, S, src_ptr, src_idx, src_val, u0_fill, E, rcv_xyz, uobs, qua, max_rounds=0,
+                        rounds=None, want_grad=True, loc=HOST):
+        """Returns (misfit, d misfit / d scale, rc)."""
+        mis, gs = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        rc = check(self._lib.adtomo_model_add_phase(self.handle, float(scale), float(h), float(tol), int(max_rounds), int(S),
+                                                    ptr(src_ptr), ptr(src_idx), ptr(src_val), float(u0_fill), int(E),
+                                                    ptr(rcv_xyz), ptr(uobs), ptr(qua), ptr(rounds), ctypes.addressof(mis),
+                                                    ctypes.addressof(gs), 1 if want_grad else 0, loc),
+                   "adtomo_model_add_phase")
+        return mis.value, gs.value, rc
+
+    def model_finish(self, lam, smooth_hor, smooth_ver, add_reg, packed, loc=HOST):
+        """packed: N+1 doubles ([d loss / d x | loss]) or None for the loss only.  Returns (loss, rc)."""
+        loss = ctypes.c_double(0.0)
+        rc = check(self._lib.adtomo_model_finish(self.handle, float(lam), int(smooth_hor), int(smooth_ver),
+                                                 1 if add_reg else 0, 0 if packed is None else 1, ctypes.addressof(loss),
+                                                 ptr(packed), loc), "adtomo_model_finish")
+        return loss.value, rc
+
+    def model_loss_grad(self, packed, x, vel0, lam, smooth_hor, smooth_ver, add_reg, h, dims, tol, S, src_ptr, src_idx,
+                        src_val, u0_fill, E, rcv_xyz, uobs, qua, max_rounds=0, rounds=None, loc=HOST):
+        """adtomo_model_loss_grad: single-phase evaluation in one call.  Returns (loss, rc)."""
+        m, n, l = dims
+        loss = ctypes.c_double(0.0)
+        rc = check(self._lib.adtomo_model_loss_grad(self.handle, ctypes.addressof(loss), ptr(packed), ptr(x), ptr(vel0),
+                                                    float(lam), int(smooth_hor), int(smooth_ver), 1 if add_reg else 0,
+                                                    float(h), m, n, l, float(tol), int(max_rounds), int(S), ptr(src_ptr),
+                                                    ptr(src_idx), ptr(src_val), float(u0_fill), int(E), ptr(rcv_xyz),
+                                                    ptr(uobs), ptr(qua), ptr(rounds), loc), "adtomo_model_loss_grad")
+        return loss.value, rc

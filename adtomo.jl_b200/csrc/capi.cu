@@ -21,6 +21,7 @@
 #include "kernels_fwd_v3.cuh"
 #include "kernels_fwd_team.cuh"
 #include "kernels_adj_team.cuh"
+#include "kernels_model.cuh"
 #include "nccl_dyn.h"
 
 using namespace adtomo;
@@ -44,8 +45,19 @@ static int fail(int code, const char *fmt, ...) {
             return fail(ADTOMO_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
     } while (0)
 
+// state of an open adtomo_model_begin .. adtomo_model_finish evaluation (model_api.inc)
+struct ModelState {
+    bool open = false;
+    int m = 0, n = 0, l = 0;
+    long long N = 0;
+    double *fvar = nullptr, *sig = nullptr, *g_fvar = nullptr, *acc = nullptr;   // acc[0]: loss so far, acc[1]: last d misfit / d scale
+    int phases = 0;
+    int flags = 0;                // worst positive status of the phases (NOT_CONVERGED / ADJOINT_FLAGGED)
+};
+
 struct adtomo_ctx {
     int device = 0;
+    ModelState model;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -512,7 +524,7 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
         if (pc->pct) pc->smem_bytes = std::max(pc->smem_bytes, (size_t)V3_STAGE_BYTES_PER_WARP * (pc->plan.NT / 32));   // cp.async staging aliases the plane
         pc->tabOffset = (int)((pc->smem_bytes + 15) & ~(size_t)15);
         pc->smem_bytes = pc->tabOffset + (sizeof(V3Slot) + sizeof(int)) * (size_t)(pc->plan.NT / 32) * pc->maxPer;
-        if (pc->smem_bytes > 100 * 1024) {           // table too large for two CTAs per SM: the round-1 sweep loop
+        if (pc->smem_bytes > (size_t)(pc->plan.NT > 512 ? 200 : 100) * 1024) {           // table too large for two CTAs per SM: the round-1 sweep loop
             pc->v3 = false;
             pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
             pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
@@ -596,10 +608,11 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
         kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol,    \
                                                                                  max_rounds, S, d_rounds, d_errs, where, order, spent); \
     } while (0)
-#define V3_LAUNCH(PCT_, STG_)                                                                                          \
+#define V3_LAUNCH(PCT_, STG_) V3_LAUNCH_NT(512, 2, PCT_, STG_)
+#define V3_LAUNCH_NT(NT_, MB_, PCT_, STG_)                                                                             \
     do {                                                                                                               \
-        auto kern = k_fwd3d_v3<512, 2, PCT_, STG_>;                                                                        \
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                       \
+        auto kern = k_fwd3d_v3<NT_, MB_, PCT_, STG_>;                                                                  \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (NT_ > 512 ? 200 : 100) * 1024));   \
         int occ = 1;                                                                                                   \
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));                           \
         if (occ < 1) occ = 1;                                                                                          \
@@ -610,6 +623,11 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     // cp.async look-ahead through shared memory pays when a CTA has its SM to itself (148 sources: 100 vs 111 ms) and
     // costs with two CTAs per SM (256 sources: 164 vs 140 ms: the L1 data pipe carries every value twice)
     const bool staged = c->v3_staged == 1 || (c->v3_staged < 0 && S <= c->num_sms);
+#ifdef ADTOMO_EXPERIMENT_NT1024
+    if (pc->v3 && P.NT > 512 && pc->pct == 72) {
+        if (staged) V3_LAUNCH_NT(1024, 1, 72, true); else V3_LAUNCH_NT(1024, 1, 72, false);
+    } else
+#endif
     if (pc->v3 && P.NT <= 512) {
         switch (pc->pct) {
 #define V3_CASE(pc_) case pc_: if (staged) V3_LAUNCH(pc_, true); else V3_LAUNCH(pc_, false); break;
@@ -624,9 +642,14 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     else if (P.NT <= 512) V2_LAUNCH(512, 2);
     else V2_LAUNCH(1024, 1);
 #undef V3_LAUNCH
+#undef V3_LAUNCH_NT
 #undef V2_LAUNCH
     phase_end(c, pk);
-    LAUNCHED(c, pc->v3 ? "k_fwd3d_v3" : "k_fwd3d_v2");
+#ifdef ADTOMO_EXPERIMENT_NT1024
+    LAUNCHED(c, pc->v3 && (P.NT <= 512 || pc->pct == 72) ? "k_fwd3d_v3" : "k_fwd3d_v2");
+#else
+    LAUNCHED(c, pc->v3 && P.NT <= 512 ? "k_fwd3d_v3" : "k_fwd3d_v2");
+#endif
     pk = phase_begin(c, PH_CONVERT);
     k2_P_to_rowmajor<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, bufs, where, dU, order);
     phase_end(c, pk);
@@ -1273,12 +1296,14 @@ extern "C" int adtomo_eikonal2d_backward(double *grad_f, const double *grad_u, c
 // ---------------------------------------------------------------------------------------
 // fused inversion step
 // ---------------------------------------------------------------------------------------
-extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, double *grad_f, const double *f, double h,
-                                            int m, int n, int l, double tol, int max_rounds, int S,
-                                            const int *src_ptr, const int *src_idx, const double *src_val,
-                                            double u0_fill, int E, const double *rcv_xyz, const double *uobs,
-                                            const double *qua, int *rounds, int loc) {
-    if (!c) return fail(ADTOMO_ERR_ARG, "null context");
+// The fused step on a locked context.  f follows loc_f and grad_f (N+1 doubles) loc_out, the source / receiver
+// tables follow loc: the on-device model (adtomo_model_*) keeps f and the gradient on the device while the tables
+// come from wherever the caller holds them.
+static int misfit_grad_core(adtomo_ctx *c, double *misfit, double *grad_f, int loc_out, const double *f, int loc_f, double h,
+                            int m, int n, int l, double tol, int max_rounds, int S,
+                            const int *src_ptr, const int *src_idx, const double *src_val,
+                            double u0_fill, int E, const double *rcv_xyz, const double *uobs,
+                            const double *qua, int *rounds, int loc) {
     if (!f || !src_ptr || !src_idx || !src_val || !rcv_xyz || !uobs || !qua)
         return fail(ADTOMO_ERR_ARG, "null input pointer");
     if (!misfit && !grad_f) return fail(ADTOMO_ERR_ARG, "no output requested");
@@ -1286,7 +1311,6 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     if (rc) return rc;
     if (E < 1) return fail(ADTOMO_ERR_ARG, "E must be >= 1");
     if (max_rounds <= 0) max_rounds = 20;
-    std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     Dims3 d{m, n, l, (long long)m * n * l};
     // sparse-source table: the row pointer is needed on the host to size the staging copies
@@ -1298,6 +1322,8 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     }
     const int nnz = hptr[S];
     if (hptr[0] != 0 || nnz < 0) return fail(ADTOMO_ERR_ARG, "src_ptr must start at 0 and be non-decreasing");
+    for (int s = 0; s < S; s++)
+        if (hptr[s + 1] < hptr[s]) return fail(ADTOMO_ERR_ARG, "src_ptr must be non-decreasing (src_ptr[%d]=%d > src_ptr[%d]=%d)", s, hptr[s], s + 1, hptr[s + 1]);
     if (loc == ADTOMO_HOST) {   // validate what we can see
         for (int q = 0; q < nnz; q++)
             if (src_idx[q] < 0 || src_idx[q] >= d.N) return fail(ADTOMO_ERR_ARG, "src_idx[%d]=%d outside the grid", q, src_idx[q]);
@@ -1309,7 +1335,7 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     }
     const double *df = nullptr, *dval = nullptr, *drcv = nullptr, *dobs = nullptr, *dqua = nullptr;
     const int *dptr, *didx;
-    if ((rc = stage_in(c, "f", f, (size_t)d.N, loc, &df))) return rc;
+    if ((rc = stage_in(c, "f", f, (size_t)d.N, loc_f, &df))) return rc;
     if ((rc = stage_in(c, "src_ptr", src_ptr, (size_t)S + 1, loc, &dptr))) return rc;
     if ((rc = stage_in(c, "src_idx", src_idx, (size_t)std::max(nnz, 1), loc, &didx))) return rc;
     if ((rc = stage_in(c, "src_val", src_val, (size_t)std::max(nnz, 1), loc, &dval))) return rc;
@@ -1345,7 +1371,7 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     WS(c, "status", int, S, dSt);
     if (grad_f) {
         WS(c, "G", double, (size_t)Sc * d.N, dG);
-        if (loc == ADTOMO_DEVICE) dSum = grad_f;
+        if (loc_out == ADTOMO_DEVICE) dSum = grad_f;
         else WS(c, "gfsum", double, d.N + 1, dSum);
         if (Sc < S) {
             WS(c, "gfsum_chunk", double, d.N, dSumChunk);
@@ -1389,7 +1415,7 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
     if (grad_f) CK(cudaMemcpyAsync(dSum + d.N, dTot, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
     c->timed = true;
-    if (grad_f && loc == ADTOMO_HOST)
+    if (grad_f && loc_out == ADTOMO_HOST)
         CK(cudaMemcpyAsync(grad_f, dSum, sizeof(double) * (d.N + 1), cudaMemcpyDeviceToHost, c->stream));
     double hm = 0.0;
     CK(cudaMemcpyAsync(&hm, dTot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1409,6 +1435,18 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
             if (hs[s] < 0) return ADTOMO_ADJOINT_FLAGGED;
     return st;
 }
+
+extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, double *grad_f, const double *f, double h,
+                                            int m, int n, int l, double tol, int max_rounds, int S,
+                                            const int *src_ptr, const int *src_idx, const double *src_val,
+                                            double u0_fill, int E, const double *rcv_xyz, const double *uobs,
+                                            const double *qua, int *rounds, int loc) {
+    if (!c) return fail(ADTOMO_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    return misfit_grad_core(c, misfit, grad_f, loc, f, loc, h, m, n, l, tol, max_rounds, S, src_ptr, src_idx, src_val, u0_fill,
+                            E, rcv_xyz, uobs, qua, rounds, loc);
+}
+#include "model_api.inc"
 
 // ---------------------------------------------------------------------------------------
 // NCCL: one all-reduce of the packed [grad_f | misfit] buffer per loss/gradient evaluation

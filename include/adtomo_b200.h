@@ -128,6 +128,39 @@ int adtomo_eikonal3d_misfit_grad(adtomo_ctx *ctx, double *misfit, double *grad_f
                                  const double *rcv_xyz, const double *uobs, const double *qua, int *rounds,
                                  int loc);
 
+/* ---- model parametrisation, chain rule and regulariser on the device --------------------- */
+/* One loss/gradient evaluation of the inversion drivers (scripts/inversion.jl:42-43,61,96-121; joint P+S:
+ * inversion_joint.jl:49-51,80,140-166) = adtomo_model_begin, one adtomo_model_add_phase per seismic phase,
+ * adtomo_model_finish.  N = m*n*l optimiser variables go in, N+1 doubles come out; the slowness fields, their
+ * gradients and the travel times stay on the device.
+ *   begin      x (var_change) and vel0, N doubles each (follow loc): fvar = 2*sigmoid(x) - 1 + vel0.
+ *   add_phase  slowness of the phase f = scale / fvar (P: scale = 1, inversion.jl:61; S: scale = pvs,
+ *              inversion_joint.jl:80) and the fused step of adtomo_eikonal3d_misfit_grad on this phase's sources
+ *              (same source / receiver arguments, following loc).  *misfit and *grad_scale (HOST doubles, may be
+ *              NULL) receive the phase's misfit and d misfit / d scale (the gradient of the joint driver's `pvs`).
+ *              want_grad == 0: misfit only.  Returns the fused step's status.
+ *   finish     loss = sum of the phases' misfits + (add_reg ? lambda * sum |fvar - box(fvar)| : 0), box = mean over
+ *              the periodic smooth_hor x smooth_hor x smooth_ver window (odd sizes; inversion.jl:107-121);
+ *              *loss (HOST, may be NULL); packed (N+1 doubles, follows loc; needed when want_grad != 0):
+ *              [d loss / d x | loss].  Returns the worst status of the phases.
+ * Multi-GPU: every rank evaluates its source shard, ONE rank passes add_reg != 0 (the reference adds the
+ * regulariser on every rank before mpi_sum, i.e. nproc times -- SURVEY 5), then packed is all-reduced.
+ * The three calls of one evaluation must not be interleaved with other evaluations on the same context. */
+int adtomo_model_begin(adtomo_ctx *ctx, const double *x, const double *vel0, int m, int n, int l, int loc);
+int adtomo_model_add_phase(adtomo_ctx *ctx, double scale, double h, double tol, int max_rounds, int S,
+                           const int *src_ptr, const int *src_idx, const double *src_val, double u0_fill, int E,
+                           const double *rcv_xyz, const double *uobs, const double *qua, int *rounds, double *misfit,
+                           double *grad_scale, int want_grad, int loc);
+int adtomo_model_finish(adtomo_ctx *ctx, double lambda, int smooth_hor, int smooth_ver, int add_reg, int want_grad,
+                        double *loss, double *packed, int loc);
+/* Single-phase evaluation (scripts/inversion.jl) in one call: begin + add_phase(scale 1) + finish.
+ * packed == NULL: loss only. */
+int adtomo_model_loss_grad(adtomo_ctx *ctx, double *loss, double *packed, const double *x, const double *vel0,
+                           double lambda, int smooth_hor, int smooth_ver, int add_reg, double h, int m, int n, int l,
+                           double tol, int max_rounds, int S, const int *src_ptr, const int *src_idx,
+                           const double *src_val, double u0_fill, int E, const double *rcv_xyz, const double *uobs,
+                           const double *qua, int *rounds, int loc);
+
 /* ---- multi-GPU: source shards + ONE all-reduce per evaluation ---------------------------- */
 /* Replaces the MPI plumbing of the drivers (mpi_bcast / mpi_sum, scripts/inversion.jl:44,123;
  * flag protocol of src/mpi_optimize.jl:11-33): one process per GPU, rank r evaluates sources
