@@ -524,7 +524,7 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
         if (pc->pct) pc->smem_bytes = std::max(pc->smem_bytes, (size_t)V3_STAGE_BYTES_PER_WARP * (pc->plan.NT / 32));   // cp.async staging aliases the plane
         pc->tabOffset = (int)((pc->smem_bytes + 15) & ~(size_t)15);
         pc->smem_bytes = pc->tabOffset + (sizeof(V3Slot) + sizeof(int)) * (size_t)(pc->plan.NT / 32) * pc->maxPer;
-        if (pc->smem_bytes > (size_t)(pc->plan.NT > 512 ? 200 : 100) * 1024) {           // table too large for two CTAs per SM: the round-1 sweep loop
+        if (pc->smem_bytes > (size_t)100 * 1024 || pc->plan.NT > 512) {   // table too large for two CTAs per SM, or more than 16 warps: the round-1 sweep loop
             pc->v3 = false;
             pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
             pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
@@ -608,11 +608,13 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
         kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, bufs, flay, flay + P.M, h, tol,    \
                                                                                  max_rounds, S, d_rounds, d_errs, where, order, spent); \
     } while (0)
-#define V3_LAUNCH(PCT_, STG_) V3_LAUNCH_NT(512, 2, PCT_, STG_)
-#define V3_LAUNCH_NT(NT_, MB_, PCT_, STG_)                                                                             \
+    const bool ragged = v3_ragged(P);      // a grid extent that is not a multiple of the warp-slot shape: lane masks needed
+    static const int v3_carveout = getenv("ADTOMO_V3_CARVEOUT") ? atoi(getenv("ADTOMO_V3_CARVEOUT")) : -1;   // tuning aid: % of L1/shared for shared memory
+#define V3_LAUNCH(PCT_, STG_)                                                                                          \
     do {                                                                                                               \
-        auto kern = k_fwd3d_v3<NT_, MB_, PCT_, STG_>;                                                                  \
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (NT_ > 512 ? 200 : 100) * 1024));   \
+        auto kern = ragged ? k_fwd3d_v3<512, 2, PCT_, STG_, true> : k_fwd3d_v3<512, 2, PCT_, STG_, false>;             \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                       \
+        if (v3_carveout >= 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, v3_carveout)); \
         int occ = 1;                                                                                                   \
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));                           \
         if (occ < 1) occ = 1;                                                                                          \
@@ -623,11 +625,6 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     // cp.async look-ahead through shared memory pays when a CTA has its SM to itself (148 sources: 100 vs 111 ms) and
     // costs with two CTAs per SM (256 sources: 164 vs 140 ms: the L1 data pipe carries every value twice)
     const bool staged = c->v3_staged == 1 || (c->v3_staged < 0 && S <= c->num_sms);
-#ifdef ADTOMO_EXPERIMENT_NT1024
-    if (pc->v3 && P.NT > 512 && pc->pct == 72) {
-        if (staged) V3_LAUNCH_NT(1024, 1, 72, true); else V3_LAUNCH_NT(1024, 1, 72, false);
-    } else
-#endif
     if (pc->v3 && P.NT <= 512) {
         switch (pc->pct) {
 #define V3_CASE(pc_) case pc_: if (staged) V3_LAUNCH(pc_, true); else V3_LAUNCH(pc_, false); break;
@@ -642,14 +639,9 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     else if (P.NT <= 512) V2_LAUNCH(512, 2);
     else V2_LAUNCH(1024, 1);
 #undef V3_LAUNCH
-#undef V3_LAUNCH_NT
 #undef V2_LAUNCH
     phase_end(c, pk);
-#ifdef ADTOMO_EXPERIMENT_NT1024
-    LAUNCHED(c, pc->v3 && (P.NT <= 512 || pc->pct == 72) ? "k_fwd3d_v3" : "k_fwd3d_v2");
-#else
-    LAUNCHED(c, pc->v3 && P.NT <= 512 ? "k_fwd3d_v3" : "k_fwd3d_v2");
-#endif
+    LAUNCHED(c, pc->v3 ? "k_fwd3d_v3" : "k_fwd3d_v2");
     pk = phase_begin(c, PH_CONVERT);
     k2_P_to_rowmajor<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, bufs, where, dU, order);
     phase_end(c, pk);

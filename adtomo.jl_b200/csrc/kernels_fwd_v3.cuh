@@ -100,6 +100,7 @@ EIK_HD int v3_duration(const Plan2 &P) {
 
 // Lane mask applied to V3Slot::meta: keeps the flag bits of the edges where this lane has NO pencil, so that a
 // flagged slot pushes the lane's W' far out of range.
+inline bool v3_ragged(const Plan2 &P) { return P.dA % V2_LA != 0 || P.dC % V2_LC != 0; }
 EIK_HD int v3_lane_mask(const Plan2 &P, const int la, const int lc) {
     const int nrb = (P.dA + V2_LA - 1) / V2_LA;
     const int bad = ((V2_LA * (nrb - 1) + la >= P.dA) ? 1 : 0) | ((V2_LC * (P.G - 1) + lc >= P.dC) ? 2 : 0);
@@ -110,8 +111,11 @@ EIK_HD int v3_lane_mask(const Plan2 &P, const int la, const int lc) {
 // off: the slot of the lane's pencil position -- ALWAYS a loadable address: for a lane without a node it lies up to
 // LA + LC rows outside the slab or up to LA - 1 slabs outside the field (the buffers are allocated with
 // v3_slack() doubles on both sides); act: the position is a grid node.
+// RG = false: the plan has no ragged edge (dA % LA == 0 and dC % LC == 0): no flag is ever set and the lane mask --
+// one more live register in a loop that already spills at 64 -- is not needed.
+template <bool RG = true>
 EIK_HD void v3_node(const Plan2 &P, const V3Slot &d, const int lamOff, const int lamWb, const int lmask, int &off, bool &act) {
-    const int wq = lamWb - (d.meta & lmask);
+    const int wq = lamWb - (RG ? (d.meta & lmask) : d.meta);
     act = (unsigned)wq < (unsigned)P.dW;
     off = lamOff + d.base;
 }
@@ -119,10 +123,59 @@ EIK_HD void v3_node(const Plan2 &P, const V3Slot &d, const int lamOff, const int
 // doubles of slack the field / slowness buffers need before and after (idle lanes load, never store, there)
 inline long long v3_slack(const Plan2 &P) { return (long long)(V2_LA + 1) * P.RS * P.PC; }
 
+// L2 eviction policies (createpolicy; they travel in the memory descriptor of the load / store, i.e. cost uniform
+// registers only).  ncu on the bench batch: the kernel reads 244 GB from DRAM per launch, 2.5x the fields it sweeps --
+// with 256 sources in flight the 126 MB L2 holds neither the level fronts nor the slowness field that ALL sources read
+// once per sweep.  ADTOMO_F_POLICY=1: slowness loads are evict_last (the two layouts of f, 29 MB at C3, stay resident);
+// ADTOMO_RESKEW_POLICY=1: the re-skew's loads and stores and the L-inf reference loads (one touch per round) are
+// evict_first.  Performance hints only.
+#ifndef ADTOMO_F_POLICY
+#define ADTOMO_F_POLICY 0
+#endif
+#ifndef ADTOMO_RESKEW_POLICY
+#define ADTOMO_RESKEW_POLICY 0
+#endif
+struct V3Pol { unsigned long long first, last; };
+#if defined(__CUDACC__)
+__device__ __forceinline__ V3Pol v3_policies() {
+    V3Pol q;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(q.first));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(q.last));
+    return q;
+}
+#endif
+// slowness of a node (read-only for the whole launch)
+EIK_HD double v3_ld_f(const double *p, const V3Pol &pol) {
+#if defined(__CUDA_ARCH__) && ADTOMO_F_POLICY == 1
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol.last));
+    return v;
+#else
+    return *p;
+#endif
+}
+// a value that is touched once (re-skew source, L-inf reference)
+EIK_HD double v3_ld_once(const double *p, const V3Pol &pol) {
+#if defined(__CUDA_ARCH__) && ADTOMO_RESKEW_POLICY >= 1
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol.first));
+    return v;
+#else
+    return *p;
+#endif
+}
+EIK_HD void v3_st_once(double *p, const double v, const V3Pol &pol) {
+#if defined(__CUDA_ARCH__) && ADTOMO_RESKEW_POLICY == 1
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol.first) : "memory");
+#else
+    *p = v;
+#endif
+}
+
 // Loads of one node (same values as v2_load).  PCT: compile-time pitch or 0.  sAb: slab stride in bytes (RS * PC * 8).
 template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT>
 EIK_HD void v3_load_old(const Plan2 &P, const long long sAb, const int off, const bool act, const double *rd,
-                        const double *__restrict__ fl, const double *cmp, V2Vals &V) {
+                        const double *__restrict__ fl, const double *cmp, V2Vals &V, const V3Pol &pol) {
     // the node's own value, the slowness and the three DOWNWIND values: nothing this sweep has written when the node's
     // level starts (they belong to this level and the next), so they may be loaded before the previous level's barrier
     const int PC = PCT ? PCT : P.PC;
@@ -131,11 +184,11 @@ EIK_HD void v3_load_old(const Plan2 &P, const long long sAb, const int off, cons
     const char *p = reinterpret_cast<const char *>(rd + off);
 #define V3_AT(ptr_, bytes_) (*reinterpret_cast<const double *>((ptr_) + (bytes_)))
     V.own = V3_AT(p, 0);
-    V.fv = fl[off];
+    V.fv = v3_ld_f(fl + off, pol);
     V.dW = V3_AT(p, offW * 8);
     V.dC = V3_AT(p, offC * 8);
     V.dA = V3_AT(p, SA * sAb);
-    V.ref = CMP ? cmp[off] : 0.0;
+    V.ref = CMP ? v3_ld_once(cmp + off, pol) : 0.0;
 }
 
 // the three UPWIND values (results of the previous level: only after that level's barrier).  off: the slot's offset
@@ -153,20 +206,23 @@ EIK_HD void v3_load_up(const Plan2 &P, const long long sAb, const int off, const
 
 template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT>
 EIK_HD void v3_load(const Plan2 &P, const long long sAb, const int off, const bool act, const double *rd, const double *wr,
-                    const double *__restrict__ fl, const double *cmp, V2Vals &V) {
-    v3_load_old<SA, SW, SC, OOP, CMP, PCT>(P, sAb, off, act, rd, fl, cmp, V);
+                    const double *__restrict__ fl, const double *cmp, V2Vals &V, const V3Pol &pol) {
+    v3_load_old<SA, SW, SC, OOP, CMP, PCT>(P, sAb, off, act, rd, fl, cmp, V, pol);
     v3_load_up<SA, SW, SC, OOP, PCT>(P, sAb, off, rd, wr, V);
 }
 
-// Re-skew index map for chunks with wc >= dC (every column wraps at most once): the same map as v2_reskew_index,
-// as lane/row parts that advance by constants.  Element (v, C): plane slot pl and slab offset go in layout sigma.
-//   cc = C (P) or dC-1-C (M);  wrapped = cc > v;  Wl = v - cc (+ wc);  pl = Wl * PS + C;  go = (w0 + Wl + cc + 1) * PC + C
-EIK_HD void v3_reskew_index(const Plan2 &P, const int sigma, const int w0, const int wc, const int v, const int C,
-                            int &pl, int &go) {
+// Re-skew of the W-chunk [w0, w0 + wc) of one slab through the plane (wc x PS doubles, un-skewed rows Wl).  Element
+// (Wl, C) lies in row w0 + 1 + Wl + cc of layout sigma, cc = C (P) or dC-1-C (M).  Thread (warp, lane = C mod 32) moves
+// the elements Wl = t0 + j * nw, j = 0, 1, ..., with t0 = (warp - cc) mod nw: at step j the lanes of a warp touch at
+// most three rows of the layout, each in a contiguous run of C (coalesced), every element exactly once, and both the
+// plane slot and the slab offset advance by constants -- no wrap, no per-element index arithmetic.
+EIK_HD void v3_reskew_start(const Plan2 &P, const int PC, const int sigma, const int w0, const int nw, const int warp,
+                            const int C, int &t0, int &pl0, int &go0) {
     const int cc = sigma > 0 ? C : P.dC - 1 - C;
-    const bool wrapped = cc > v;
-    pl = (C - cc * P.PS) + v * P.PS + (wrapped ? wc * P.PS : 0);
-    go = (C + (w0 + 1) * P.PC) + v * P.PC + (wrapped ? wc * P.PC : 0);
+    t0 = (warp - cc) % nw;
+    if (t0 < 0) t0 += nw;
+    pl0 = t0 * P.PS + C;
+    go0 = (w0 + 1 + cc + t0) * PC + C;
 }
 
 #if defined(__CUDACC__)
@@ -187,67 +243,66 @@ __device__ __forceinline__ void v3_build_table(const Plan2 &P, const int PC, V3S
     }
 }
 
-// Re-skew pass for chunks with wc >= dC: lane = column C, a warp takes virtual rows v = warp, warp + nw, ...; eight
-// elements in flight per thread, ~7 instructions per element (v2_reskew_pass: ~19, 18 % of the kernel's instructions).
-template <int PHASE>
-__device__ __forceinline__ void v3_reskew_pass(const Plan2 &P, const double *s, double *d, const int sigma,
-                                               double *plane, const int w0, const int wc) {
+// One phase of the re-skew of a chunk (see v3_reskew_start).  PHASE 0: rows of layout sigma -> plane; 1: plane -> rows
+// of layout sigma.  NW: warps of the CTA (0 = run time), PCT: row pitch (0 = run time): with both known the eight
+// elements a thread has in flight sit at immediate offsets of one address.  The round-2 profile
+// (profiles/r02_ncu_summary_v3b.json) had the previous form of this pass at 22 % of the kernel's instructions
+// (~50 per element and phase: the index map was rematerialised for every element under the 64-register cap).
+template <int PHASE, int NW, int PCT>
+__device__ __forceinline__ void v3_reskew_rows(const Plan2 &P, const double *s, double *d, const int sigma, double *plane,
+                                               const int w0, const int wc, const V3Pol &pol) {
     constexpr int U = 8;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int PC = P.PC, PS = P.PS, wrapG = wc * PC, wrapP = wc * PS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = NW ? NW : (int)(blockDim.x >> 5);
+    const int PC = PCT ? PCT : P.PC;
+    const int stepP = nw * P.PS, stepG = nw * PC;
     for (int C = lane; C < P.dC; C += 32) {
-        const int cc = sigma > 0 ? C : P.dC - 1 - C;
-        const int plc = C - cc * PS, glc = C + (w0 + 1) * PC;
-        for (int v0 = warp; v0 < wc; v0 += U * nw) {
-            int pls[U], gos[U];
+        int t, pl, go;
+        v3_reskew_start(P, PC, sigma, w0, nw, warp, C, t, pl, go);
+        const double *gs = s + go;
+        double *gd = d + go;
+        double *pp = plane + pl;
+        for (; t < wc; t += U * nw, gs += U * stepG, gd += U * stepG, pp += U * stepP) {
             double x[U];
 #pragma unroll
             for (int j = 0; j < U; j++) {
-                const int v = v0 + j * nw;
-                const bool wrapped = cc > v;
-                pls[j] = plc + v * PS + (wrapped ? wrapP : 0);
-                gos[j] = glc + v * PC + (wrapped ? wrapG : 0);
-            }
-#pragma unroll
-            for (int j = 0; j < U; j++) {
                 x[j] = 0.0;
-                if (v0 + j * nw < wc) x[j] = PHASE == 0 ? s[gos[j]] : plane[pls[j]];
+                if (t + j * nw < wc) x[j] = PHASE == 0 ? v3_ld_once(gs + j * stepG, pol) : pp[j * stepP];
             }
 #pragma unroll
             for (int j = 0; j < U; j++)
-                if (v0 + j * nw < wc) {
-                    if (PHASE == 0) plane[pls[j]] = x[j];
-                    else d[gos[j]] = x[j];
+                if (t + j * nw < wc) {
+                    if (PHASE == 0) pp[j * stepP] = x[j];
+                    else v3_st_once(gd + j * stepG, x[j], pol);
                 }
         }
     }
 }
 
 // slabs A in [A0, A1); same contract as v2_reskew
+template <int PCT>
 __device__ __forceinline__ void v3_reskew(const Plan2 &P, const double *src, double *dst, const int sigmaFrom,
-                                          double *plane, const int A0, const int A1) {
+                                          double *plane, const int A0, const int A1, const V3Pol &pol) {
+    const int PC = PCT ? PCT : P.PC;
     for (int A = A0; A < A1; A++) {
-        const double *s = src + (long long)(A + 1) * P.RS * P.PC;
-        double *d = dst + (long long)(A + 1) * P.RS * P.PC;
+        const double *s = src + (long long)(A + 1) * P.RS * PC;
+        double *d = dst + (long long)(A + 1) * P.RS * PC;
         for (int w0 = 0; w0 < P.dW; w0 += P.WCH) {
             const int wc = (P.dW - w0 < P.WCH) ? P.dW - w0 : P.WCH;
-            if (wc >= P.dC) {
-                v3_reskew_pass<0>(P, s, d, sigmaFrom, plane, w0, wc);
-                __syncthreads();
-                v3_reskew_pass<1>(P, s, d, -sigmaFrom, plane, w0, wc);
-            } else {
-                v2_reskew_pass<0>(P, s, d, sigmaFrom, plane, w0, wc);
-                __syncthreads();
-                v2_reskew_pass<1>(P, s, d, -sigmaFrom, plane, w0, wc);
-            }
+            if (blockDim.x == 512) v3_reskew_rows<0, 16, PCT>(P, s, d, sigmaFrom, plane, w0, wc, pol);
+            else v3_reskew_rows<0, 0, PCT>(P, s, d, sigmaFrom, plane, w0, wc, pol);
+            __syncthreads();
+            if (blockDim.x == 512) v3_reskew_rows<1, 16, PCT>(P, s, d, -sigmaFrom, plane, w0, wc, pol);
+            else v3_reskew_rows<1, 0, PCT>(P, s, d, -sigmaFrom, plane, w0, wc, pol);
             __syncthreads();
         }
     }
 }
 
-template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT>
+template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT, bool RG>
 __device__ __forceinline__ void v3_sweep(const Plan2 &P, V3Slot *tab, int *tabS, const int maxPer, const double *rd, double *wr,
-                                         const double *__restrict__ fl, const double *cmp, const double h, double &err) {
+                                         const double *__restrict__ fl, const double *cmp, const double h, double &err,
+                                         const V3Pol &pol) {
     const int PC = PCT ? PCT : P.PC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const V2Lane L = v2_lane_setup<SA, SW, SC>(P, lane);      // P.PC == PC (the plan was built for this pitch)
@@ -284,8 +339,8 @@ __device__ __forceinline__ void v3_sweep(const Plan2 &P, V3Slot *tab, int *tabS,
         V3Slot d__;                                                                              \
         d__.base = d2__.x; d__.meta = d2__.y;                                                    \
         int off__; bool act__;                                                                   \
-        v3_node(P, d__, lamOff, lamWb, lmask, off__, act__);                                     \
-        v3_load<SA, SW, SC, OOP, CMP, PCT>(P, sAb, off__, act__, rd, wr, fl, cmp, V_);           \
+        v3_node<RG>(P, d__, lamOff, lamWb, lmask, off__, act__);                                 \
+        v3_load<SA, SW, SC, OOP, CMP, PCT>(P, sAb, off__, act__, rd, wr, fl, cmp, V_, pol);      \
     } while (0)
         int left = tail - head;
         if (left > 0) {
@@ -326,7 +381,7 @@ __device__ __forceinline__ void v3_cp_wait() { asm volatile("cp.async.wait_group
 
 constexpr int V3_STAGE_BYTES_PER_WARP = 2 * 8 * 32 * 8;
 
-template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT>
+template <int SA, int SW, int SC, bool OOP, bool CMP, int PCT, bool RG>
 __device__ __forceinline__ void v3_sweep_staged(const Plan2 &P, V3Slot *tab, int *tabS, const int maxPer, double *stage,
                                                 const double *rd, double *wr, const double *__restrict__ fl,
                                                 const double *cmp, const double h, double &err) {
@@ -367,7 +422,7 @@ __device__ __forceinline__ void v3_sweep_staged(const Plan2 &P, V3Slot *tab, int
         V3Slot d__;                                                                              \
         d__.base = d2__.x; d__.meta = d2__.y;                                                    \
         int off__; bool act__;                                                                   \
-        v3_node(P, d__, lamOff, lamWb, lmask, off__, act__);                                     \
+        v3_node<RG>(P, d__, lamOff, lamWb, lmask, off__, act__);                                 \
         off_ = act__ ? off__ : -1;                                                               \
         const unsigned s__ = sb + (par_);                                                        \
         const char *p__ = reinterpret_cast<const char *>(rd + off__);                            \
@@ -415,7 +470,7 @@ __device__ __forceinline__ void v3_sweep_staged(const Plan2 &P, V3Slot *tab, int
 // Same contract as k_fwd3d_v2 (buffers, order, rounds, errs, where, spent); the field and slowness buffers have
 // v3_slack() loadable doubles on both sides.  Dynamic shared memory: the re-skew plane (WCH x PS doubles) followed by
 // the slot table (nw x maxPer int2, then nw x maxPer int).
-template <int NTMAX, int MINB, int PCT, bool STG>
+template <int NTMAX, int MINB, int PCT, bool STG, bool RG>
 __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const int tabOffset, const int maxPer, double *bufs,
                                                           const double *__restrict__ fP, const double *__restrict__ fM,
                                                           const double h, const double tol, const int max_rounds,
@@ -426,6 +481,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const i
     __shared__ double red[32];
     V3Slot *tab = reinterpret_cast<V3Slot *>(reinterpret_cast<char *>(plane) + tabOffset);
     int *tabS = reinterpret_cast<int *>(tab + (blockDim.x >> 5) * maxPer);
+    const V3Pol pol = v3_policies();
     for (int src = blockIdx.x; src < S; src += gridDim.x) {
         double *B3 = bufs + (long long)src * 3 * P.M;
         int o = 0, a = 1;          // layout P: round-start field, working field;  buffer 2: layout M
@@ -442,16 +498,16 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const i
                 if (sw > 0 && sigma != state) {
                     double *dst = state > 0 ? Bz : Ba;
                     __syncthreads();
-                    v3_reskew(P, w, dst, state, plane, 0, P.dA);
+                    v3_reskew<PCT>(P, w, dst, state, plane, 0, P.dA, pol);
                     w = dst;
                     state = sigma;
                 }
 #define V3_CALL(a_, w_, c_, oop_, cmp_)                                                                                  \
     do {                                                                                                                 \
         if constexpr (STG && PCT != 0)                                                                                   \
-            v3_sweep_staged<a_, w_, c_, oop_, cmp_, PCT>(P, tab, tabS, maxPer, plane, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
+            v3_sweep_staged<a_, w_, c_, oop_, cmp_, PCT, RG>(P, tab, tabS, maxPer, plane, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
         else                                                                                                             \
-            v3_sweep<a_, w_, c_, oop_, cmp_, PCT>(P, tab, tabS, maxPer, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
+            v3_sweep<a_, w_, c_, oop_, cmp_, PCT, RG>(P, tab, tabS, maxPer, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err, pol); \
     } while (0)
                 V2_DISPATCH(P, sw, V3_CALL);
 #undef V3_CALL

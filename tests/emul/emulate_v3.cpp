@@ -1,6 +1,6 @@
 // tests/emul/emulate_v3.cpp -- TEST INFRASTRUCTURE.  Serial host emulation of the batch sweep kernel
 // (adtomo.jl_b200/csrc/kernels_fwd_v3.cuh): the kernel's OWN per-thread functions (v3_rank / v3_make_slot /
-// v3_node_off / v3_load, v2_prep / v2_solve, v2_reskew_elem) compiled for the host and run for every warp and lane
+// v3_node / v3_load, v2_prep / v2_solve, v3_reskew_start) compiled for the host and run for every warp and lane
 // in turn, level by level, with the same plan, slot table, [head, tail) window and round loop.  Inside a level the
 // threads only read level-1 / level+1 data and write level data, so the serial order is equivalent to the parallel one.
 // It also checks what the kernel relies on: every node is updated exactly once per sweep, and the live slots of a
@@ -56,11 +56,17 @@ static void sweep_t(const Plan2 &P, const double *rd, double *wr, const double *
                     V2Vals V;
                     int off;
                     bool act;
-                    v3_node(P, mine[j], L[lane].offc + lam * SW * P.PC, L[lane].wqc + lam + V3_BIAS, lmask[lane], off, act);
+                    v3_node<true>(P, mine[j], L[lane].offc + lam * SW * P.PC, L[lane].wqc + lam + V3_BIAS, lmask[lane], off, act);
+                    if (!v3_ragged(P)) {      // the kernel's mask-free form must agree where it is used
+                        int off2;
+                        bool act2;
+                        v3_node<false>(P, mine[j], L[lane].offc + lam * SW * P.PC, L[lane].wqc + lam + V3_BIAS, lmask[lane], off2, act2);
+                        if (off2 != off || act2 != act) g_bad_reskew = true;
+                    }
                     const long long reach = (long long)P.RS * P.PC + P.PC + 1;      // farthest neighbour of a slot
                     if (off - reach < -v3_slack(P) || off + reach >= P.M + v3_slack(P)) g_out_of_slack = true;
                     // the PCT = 0 (run-time pitch) path: identical arithmetic, the pitch only feeds addresses
-                    v3_load<SA, SW, SC, OOP, CMP, 0>(P, sAb, off, act, rd, wr, fl, cmp, V);
+                    v3_load<SA, SW, SC, OOP, CMP, 0>(P, sAb, off, act, rd, wr, fl, cmp, V, V3Pol{0, 0});
                     if (act) g_visits++;
                     v2_finish<OOP, CMP>(V, wr, h, err);
                 }
@@ -69,25 +75,37 @@ static void sweep_t(const Plan2 &P, const double *rd, double *wr, const double *
     }
 }
 
+// The kernel's re-skew: every thread (warp, lane) walks its elements t0, t0 + nw, ... of every column it owns
+// (v3_reskew_start); here for all warps and lanes in turn.  Checks that every element of the chunk is moved exactly once.
 static void reskew(const Plan2 &P, const double *src, double *dst, int sigmaFrom, std::vector<double> &plane) {
+    const int nw = P.NT / 32;
+    std::vector<int> hits((size_t)P.WCH * P.dC);
     for (int A = 0; A < P.dA; A++) {
         const long long slab = (long long)(A + 1) * P.RS * P.PC;
         for (int w0 = 0; w0 < P.dW; w0 += P.WCH) {
             const int wc = std::min(P.WCH, P.dW - w0);
-            for (int phase = 0; phase < 2; phase++)
-                for (int v = 0; v < wc; v++)
-                    for (int C = 0; C < P.dC; C++) {
-                        if (wc >= P.dC) {       // the kernel's fast index map: must agree with the general one
-                            int pl, go, pl2, go2;
-                            v3_reskew_index(P, phase == 0 ? sigmaFrom : -sigmaFrom, w0, wc, v, C, pl, go);
-                            v2_reskew_index(P, phase == 0 ? sigmaFrom : -sigmaFrom, w0, wc, v, C, pl2, go2);
-                            if (pl != pl2 || go != go2) g_bad_reskew = true;
-                            if (phase == 0) plane[pl] = src[slab + go];
-                            else dst[slab + go] = plane[pl];
-                        } else {
-                            v2_reskew_elem(P, src, dst, sigmaFrom, plane.data(), slab, w0, wc, phase, v, C);
+            for (int phase = 0; phase < 2; phase++) {
+                std::fill(hits.begin(), hits.end(), 0);
+                const int sigma = phase == 0 ? sigmaFrom : -sigmaFrom;
+                for (int warp = 0; warp < nw; warp++)
+                    for (int lane = 0; lane < 32; lane++)
+                        for (int C = lane; C < P.dC; C += 32) {
+                            int t, pl, go;
+                            v3_reskew_start(P, P.PC, sigma, w0, nw, warp, C, t, pl, go);
+                            for (; t < wc; t += nw, pl += nw * P.PS, go += nw * P.PC) {
+                                int pl2, go2;      // the general index map of the round-1 kernel: same element, same slots
+                                const int cc = sigma > 0 ? C : P.dC - 1 - C;
+                                v2_reskew_index(P, sigma, w0, wc, (t + cc) % wc, C, pl2, go2);
+                                if (pl != pl2 || go != go2 || pl != t * P.PS + C) g_bad_reskew = true;
+                                hits[(size_t)t * P.dC + C]++;
+                                if (phase == 0) plane[pl] = src[slab + go];
+                                else dst[slab + go] = plane[pl];
+                            }
                         }
-                    }
+                for (int t = 0; t < wc; t++)
+                    for (int C = 0; C < P.dC; C++)
+                        if (hits[(size_t)t * P.dC + C] != 1) g_bad_reskew = true;
+            }
         }
     }
 }
