@@ -130,11 +130,17 @@ def check(rc, what=""):
 
 
 def ptr(a):
-    """void* of a numpy array (host) or a torch tensor (host or CUDA); None -> NULL."""
+    """void* of a numpy array (host) or a torch tensor (host or CUDA); None -> NULL.
+    The library works on its own stream: a CUDA tensor that torch kernels may still be writing (or reading) is made
+    safe by synchronising torch's current stream of that device first -- a host-side wait of microseconds when nothing
+    is pending, and the call that follows synchronises anyway."""
     if a is None:
         return None
     if isinstance(a, np.ndarray):
         return a.ctypes.data
+    if getattr(a, "is_cuda", False):
+        import torch
+        torch.cuda.current_stream(a.device).synchronize()
     return a.data_ptr()   # torch.Tensor
 
 

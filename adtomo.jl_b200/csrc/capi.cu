@@ -19,6 +19,7 @@
 #include "kernels_fwd_v1.cuh"
 #include "kernels_fwd_v2.cuh"
 #include "kernels_fwd_v3.cuh"
+#include "kernels_fwd_v4.cuh"
 #include "kernels_fwd_team.cuh"
 #include "kernels_adj_team.cuh"
 #include "kernels_model.cuh"
@@ -83,6 +84,7 @@ struct adtomo_ctx {
     long long batch_id = 0;                     // adtomo_set_batch_id: names the source batch of the following calls
     const char *last_fwd_kernel = "";           // name of the last 3D forward sweep kernel launched (adtomo_last_forward_kernel)
     int v3_mode = 1;                            // ADTOMO_V3: 1 (default) batch sweeps of kernels_fwd_v3.cuh with menu pitch, 2 same with run-time pitch, 0 the round-1 sweep loop (cross-check)
+    int v4_mode = 0;                            // ADTOMO_V4: 1 the slot-block sweep of kernels_fwd_v4.cuh where the grid allows it (bit-exact, measured slower: 2.4x the DRAM reads), 0 (default) never
     int v3_staged = -1;                         // ADTOMO_V3_STAGED: cp.async look-ahead through shared memory: -1 automatic (one CTA per SM), 0 never, 1 always
     int v2_occ = 0;                             // tuning aid: ADTOMO_V2_OCC caps the CTAs per SM of the skewed-pencil kernel
     std::vector<struct Plan2Cache *> plans2;    // skewed-pencil plans, one per grid shape
@@ -213,6 +215,8 @@ extern "C" int adtomo_create(adtomo_ctx **out, int device) {
     c->v3_mode = v3m ? atoi(v3m) : 1;
     const char *v3s = getenv("ADTOMO_V3_STAGED");
     c->v3_staged = v3s ? atoi(v3s) : -1;
+    const char *v4m = getenv("ADTOMO_V4");
+    c->v4_mode = v4m ? atoi(v4m) : 0;
     const char *fvv = getenv("ADTOMO_FWD_VARIANT");
     c->fwd_variant = fvv ? atoi(fvv) : 0;
     const char *fcl = getenv("ADTOMO_FORCE_CLUSTER");
@@ -625,7 +629,28 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     // cp.async look-ahead through shared memory pays when a CTA has its SM to itself (148 sources: 100 vs 111 ms) and
     // costs with two CTAs per SM (256 sources: 164 vs 140 ms: the L1 data pipe carries every value twice)
     const bool staged = c->v3_staged == 1 || (c->v3_staged < 0 && S <= c->num_sms);
-    if (pc->v3 && P.NT <= 512) {
+    // slot-block sweep (kernels_fwd_v4.cuh): 4 x 8 patches, no ragged edge, compile-time pitch, 16 warps
+    const bool v4 = pc->v3 && c->v4_mode && pc->pct != 0 && P.NT == 512 && v4_supported(P) && c->v3_staged != 1;
+#define V4_LAUNCH(PCT_)                                                                                                \
+    do {                                                                                                               \
+        auto kern = k_fwd3d_v4<512, 2, PCT_>;                                                                          \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                       \
+        int occ = 1;                                                                                                   \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));                           \
+        if (occ < 1) occ = 1;                                                                                          \
+        if (c->v2_occ > 0 && occ > c->v2_occ) occ = c->v2_occ;                                                         \
+        kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, pc->tabOffset, bufs, flay, flay + P.M, h, tol, \
+                                                                                 max_rounds, S, d_rounds, d_errs, where, order, spent); \
+    } while (0)
+    if (v4) {
+        switch (pc->pct) {
+#define V4_CASE(pc_) case pc_: V4_LAUNCH(pc_); break;
+            V3_PC_MENU(V4_CASE)
+#undef V4_CASE
+            default: return fail(ADTOMO_ERR_ARG, "internal: no slot-block kernel for pitch %d", pc->pct);
+        }
+    }
+    else if (pc->v3 && P.NT <= 512) {
         switch (pc->pct) {
 #define V3_CASE(pc_) case pc_: if (staged) V3_LAUNCH(pc_, true); else V3_LAUNCH(pc_, false); break;
             V3_PC_MENU(V3_CASE)
@@ -639,9 +664,10 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     else if (P.NT <= 512) V2_LAUNCH(512, 2);
     else V2_LAUNCH(1024, 1);
 #undef V3_LAUNCH
+#undef V4_LAUNCH
 #undef V2_LAUNCH
     phase_end(c, pk);
-    LAUNCHED(c, pc->v3 ? "k_fwd3d_v3" : "k_fwd3d_v2");
+    LAUNCHED(c, v4 ? "k_fwd3d_v4" : pc->v3 ? "k_fwd3d_v3" : "k_fwd3d_v2");
     pk = phase_begin(c, PH_CONVERT);
     k2_P_to_rowmajor<<<dim3(std::min(eb, 64), S), 256, 0, c->stream>>>(P, bufs, where, dU, order);
     phase_end(c, pk);
@@ -1334,6 +1360,19 @@ static int misfit_grad_core(adtomo_ctx *c, double *misfit, double *grad_f, int l
     if ((rc = stage_in(c, "rcv", rcv_xyz, (size_t)3 * E, loc, &drcv))) return rc;
     if ((rc = stage_in(c, "uobs", uobs, (size_t)S * E, loc, &dobs))) return rc;
     if ((rc = stage_in(c, "qua", qua, (size_t)S * E, loc, &dqua))) return rc;
+    if (loc == ADTOMO_DEVICE) {   // the same checks for tables the host cannot see
+        int *dflag;
+        WS(c, "tabflag", int, 1, dflag);
+        CK(cudaMemsetAsync(dflag, 0, sizeof(int), c->stream));
+        const int nq = std::max(nnz, E);
+        k_validate_tables<<<(nq + 255) / 256, 256, 0, c->stream>>>(didx, nnz, d.N, drcv, E, m, n, l, dflag);
+        LAUNCHED(c, "k_validate_tables");
+        int hflag = 0;
+        CK(cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (hflag & 1) return fail(ADTOMO_ERR_ARG, "src_idx holds an index outside the grid (device table)");
+        if (hflag & 2) return fail(ADTOMO_ERR_ARG, "a receiver lies outside the grid (device table)");
+    }
 
     // per-source device footprint: U, U0, G, X (8 B each) + code (1 B)
     int Sc;

@@ -332,7 +332,11 @@ __device__ __forceinline__ void v3_sweep(const Plan2 &P, V3Slot *tab, int *tabS,
         // The loads of the warp's next slot are issued before the current slot's arithmetic (software pipelining by
         // hand).  Measured and rejected (profiles/r02_v3_phase_cycles.json): a second register set (spills at 64
         // registers; CTAs of 384 / 256 threads with 80 / 114 registers lose more to the missing warps), carrying the
-        // look-ahead across the level barrier, L2 prefetch of the next level's rows.
+        // look-ahead across the level barrier, L2 prefetch of the next level's rows; round 2, second session
+        // (profiles/r02_forward_experiments.json): the three COLD values of a slot (slowness, downwind W / A) asked for
+        // two slots ahead and across the barrier with the five warm ones loaded at use (161.8 vs 137.5 ms: the warm
+        // values are not reliable L1 hits), L2 eviction hints and a persisting window for the slowness (no change in
+        // DRAM bytes), a smaller re-skew plane for more L1 (slower).
 #define V3_LOAD(V_)                                                                              \
     do {                                                                                         \
         const int2 d2__ = *dp++;                                                                 \

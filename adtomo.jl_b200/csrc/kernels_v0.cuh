@@ -156,6 +156,21 @@ __global__ void k_fill(double *__restrict__ p, const long long n, const double v
 
 // One thread per sparse entry, in list order per source (later entries win, like the Julia
 // assignments of inversion.jl:52-60 -- duplicates carry identical values there).
+// Device-resident source / receiver tables cannot be checked on the host: flag[0] |= 1 for a source index outside the
+// grid, |= 2 for a receiver outside it (the scatter / sampling kernels would write or read out of bounds).
+__global__ void k_validate_tables(const int *__restrict__ src_idx, const int nnz, const long long N,
+                                  const double *__restrict__ rcv, const int E, const int m, const int n, const int l,
+                                  int *__restrict__ flag) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    if (q < nnz && (src_idx[q] < 0 || src_idx[q] >= N)) bad |= 1;
+    if (q < E) {
+        const double x = rcv[3 * q], y = rcv[3 * q + 1], z = rcv[3 * q + 2];
+        if (!(x >= 0 && x <= m - 1 && y >= 0 && y <= n - 1 && z >= 0 && z <= l - 1)) bad |= 2;
+    }
+    if (bad) atomicOr(flag, bad);
+}
+
 __global__ void k_scatter_sources(double *__restrict__ U0, const int *__restrict__ src_ptr,
                                   const int *__restrict__ src_idx, const double *__restrict__ src_val,
                                   const long long N, const int S) {

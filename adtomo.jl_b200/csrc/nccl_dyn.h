@@ -34,6 +34,9 @@ struct NcclApi {
         GetErrorString = (const char *(*)(int))dlsym(handle, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) {
             *why = "libnccl lacks a required symbol";
+            dlclose(handle);       // a later call must not take the half-resolved table for a loaded library
+            handle = nullptr;
+            GetUniqueId = nullptr; CommInitRank = nullptr; CommDestroy = nullptr; AllReduce = nullptr; GetErrorString = nullptr;
             return false;
         }
         return true;

@@ -21,6 +21,13 @@
  *     negative code otherwise.
  *   - `loc` arguments: ADTOMO_HOST (pointers are host memory; the library stages the copies
  *     on its stream) or ADTOMO_DEVICE (pointers are device memory on the context's device).
+ *     The library works on the context's OWN stream (adtomo_stream): device buffers that other
+ *     streams are still writing or reading must be complete before the call (synchronise the
+ *     producing stream, or make adtomo_stream wait on an event); every entry point returns
+ *     after its results are complete.  Device-resident index / coordinate tables are checked
+ *     on the device (out-of-range entries give ADTOMO_ERR_ARG like host tables do).
+ *   - sums that involve atomics (the fused misfit and its sparse right-hand side) are
+ *     reproducible to ~1e-16 relative, not bit for bit, from run to run.
  */
 #ifndef ADTOMO_B200_H
 #define ADTOMO_B200_H

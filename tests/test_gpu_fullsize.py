@@ -59,13 +59,15 @@ print("fullsize ok", grid, nsrc, list(rounds), "grad rel err %.1e" % err)
 
 @pytest.mark.parametrize("grid,nsrc,env,kernel", [
     ("c3", 4, {"ADTOMO_FORCE_V2": "1"}, "k_fwd3d_v3"),                               # the kernel of the bench line
-    ("c3", 4, {"ADTOMO_FORCE_V2": "1", "ADTOMO_V3_STAGED": "1"}, "k_fwd3d_v3"),       # its one-CTA-per-SM variant
     ("c3", 4, {"ADTOMO_FORCE_V2": "1", "ADTOMO_ADJ_SPARSE": "1"}, "k_fwd3d_v3"),      # ... with the active-set adjoint the bench batch runs on
+    ("c3", 4, {"ADTOMO_FORCE_V2": "1", "ADTOMO_V3_STAGED": "1"}, "k_fwd3d_v3"),       # its one-CTA-per-SM variant
+    ("c3", 4, {"ADTOMO_FORCE_V2": "1", "ADTOMO_V4": "1"}, "k_fwd3d_v4"),              # slot-block sweep (register hand-over; opt-in)
     ("c3", 2, {"ADTOMO_FORCE_V2": "1", "ADTOMO_V3": "2"}, "k_fwd3d_v3"),              # run-time row pitch
     ("c3", 2, {"ADTOMO_FORCE_V2": "1", "ADTOMO_V3": "0"}, "k_fwd3d_v2"),              # the round-1 sweep loop
     ("c3", 2, {"ADTOMO_TEAM": "0"}, "k_fwd3d_v1"),                                    # level-major kernel, one SM per source
     ("c3", 2, {}, "k_fwd3d_team"),                                                    # what the library picks for 2 sources
     ("c4", 4, {"ADTOMO_FORCE_V2": "1", "ADTOMO_ADJ_SPARSE": "1"}, "k_fwd3d_v3"),      # the kernels of bench --config c4
+    ("c4", 2, {"ADTOMO_FORCE_V2": "1", "ADTOMO_V4": "1"}, "k_fwd3d_v4"),
     ("c4", 1, {"ADTOMO_TEAM": "0"}, "k_fwd3d_v1"),                                    # cluster kernel at its natural size
 ])
 def test_bench_size_parity(tmp_path, grid, nsrc, env, kernel):
