@@ -471,6 +471,38 @@ __device__ __forceinline__ void v3_sweep_staged(const Plan2 &P, V3Slot *tab, int
     }
 }
 
+// One round (the 8 sweeps with their re-skews, Eikonal3D.cpp:59-68) of the source whose buffers start at B3; o / a: the
+// buffers that hold the round-start field / receive the result.  Returns the round's L-inf change (block-uniform).
+template <int PCT, bool STG, bool RG>
+__device__ __forceinline__ double v3_round(const Plan2 &P, V3Slot *tab, int *tabS, const int maxPer, double *plane, double *red,
+                                           double *B3, const int o, const int a, const double *__restrict__ fP,
+                                           const double *__restrict__ fM, const double h, const V3Pol &pol) {
+    double err = 0.0;
+    double *Bo = B3 + o * P.M, *Ba = B3 + a * P.M, *Bz = B3 + 2 * P.M;
+    int state = 1;                        // layout of the working field
+    double *w = Ba;
+    for (int sw = 0; sw < 8; sw++) {
+        const int sigma = P.sg[sw][1] * P.sg[sw][2];
+        if (sw > 0 && sigma != state) {
+            double *dst = state > 0 ? Bz : Ba;
+            __syncthreads();
+            v3_reskew<PCT>(P, w, dst, state, plane, 0, P.dA, pol);
+            w = dst;
+            state = sigma;
+        }
+#define V3_CALL(a_, w_, c_, oop_, cmp_)                                                                                  \
+    do {                                                                                                                 \
+        if constexpr (STG && PCT != 0)                                                                                   \
+            v3_sweep_staged<a_, w_, c_, oop_, cmp_, PCT, RG>(P, tab, tabS, maxPer, plane, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
+        else                                                                                                             \
+            v3_sweep<a_, w_, c_, oop_, cmp_, PCT, RG>(P, tab, tabS, maxPer, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err, pol); \
+    } while (0)
+        V2_DISPATCH(P, sw, V3_CALL);
+#undef V3_CALL
+    }
+    return v2_block_max(err, red);
+}
+
 // Same contract as k_fwd3d_v2 (buffers, order, rounds, errs, where, spent); the field and slowness buffers have
 // v3_slack() loadable doubles on both sides.  Dynamic shared memory: the re-skew plane (WCH x PS doubles) followed by
 // the slot table (nw x maxPer int2, then nw x maxPer int).
@@ -489,34 +521,10 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_v3(const Plan2 P, const i
     for (int src = blockIdx.x; src < S; src += gridDim.x) {
         double *B3 = bufs + (long long)src * 3 * P.M;
         int o = 0, a = 1;          // layout P: round-start field, working field;  buffer 2: layout M
-        double *Bz = B3 + 2 * P.M;
         int r = 0;
         bool conv = false;
         while (r < max_rounds) {
-            double err = 0.0;
-            double *Bo = B3 + o * P.M, *Ba = B3 + a * P.M;
-            int state = 1;                        // layout of the working field
-            double *w = Ba;
-            for (int sw = 0; sw < 8; sw++) {
-                const int sigma = P.sg[sw][1] * P.sg[sw][2];
-                if (sw > 0 && sigma != state) {
-                    double *dst = state > 0 ? Bz : Ba;
-                    __syncthreads();
-                    v3_reskew<PCT>(P, w, dst, state, plane, 0, P.dA, pol);
-                    w = dst;
-                    state = sigma;
-                }
-#define V3_CALL(a_, w_, c_, oop_, cmp_)                                                                                  \
-    do {                                                                                                                 \
-        if constexpr (STG && PCT != 0)                                                                                   \
-            v3_sweep_staged<a_, w_, c_, oop_, cmp_, PCT, RG>(P, tab, tabS, maxPer, plane, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err); \
-        else                                                                                                             \
-            v3_sweep<a_, w_, c_, oop_, cmp_, PCT, RG>(P, tab, tabS, maxPer, oop_ ? Bo : w, w, sigma > 0 ? fP : fM, Bo, h, err, pol); \
-    } while (0)
-                V2_DISPATCH(P, sw, V3_CALL);
-#undef V3_CALL
-            }
-            const double e = v2_block_max(err, red);
+            const double e = v3_round<PCT, STG, RG>(P, tab, tabS, maxPer, plane, red, B3, o, a, fP, fM, h, pol);
             if (threadIdx.x == 0 && errs) errs[(long long)order[src] * max_rounds + r] = e;
             r++;
             const int oo = o; o = a; a = oo;      // the result (in a) becomes next round's round-start field
