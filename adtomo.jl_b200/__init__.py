@@ -12,4 +12,4 @@ from .capi import (AdtomoError, Context, LIB_PATH, build_library, load_library, 
 from .eikonal_op import (eikonal, eikonal3d, eikonal_forward, eikonal_backward, eikonal3d_forward,  # noqa: F401
                          eikonal3d_backward)
 from .inversion import (corner_sources, InversionProblem, shard_sources)  # noqa: F401
-from .optimize import gpu_optimize, VelocityModel, DeviceVelocityModel, box_filter_periodic, save_checkpoint  # noqa: F401
+from .optimize import gpu_optimize, gpu_optimize_model, VelocityModel, DeviceVelocityModel, box_filter_periodic, save_checkpoint  # noqa: F401

@@ -37,6 +37,7 @@
 // Buffers per source: three fields o/a (layout P) and z (layout M).  Sweep 1 of a round reads o and
 // writes a (o stays as the round-start field for the L-inf stopping test, fused into sweep 8).
 #pragma once
+#include <cstdlib>
 #include "eik_core.h"
 
 namespace adtomo {
@@ -593,7 +594,9 @@ inline bool v2_build_plan(Plan2 &P, int m, int n, int l, int nwarps, size_t plan
     double best = -1.0;
     int bestRole[3] = {0, 1, 2};
     static const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    static const int forced = getenv("ADTOMO_V2_PERM") ? atoi(getenv("ADTOMO_V2_PERM")) : -1;   // tuning aid: role assignment 0..5
     for (int p = 0; p < 6; p++) {
+        if (forced >= 0 && p != forced) continue;
         const int dA = ext[perms[p][0]], dW = ext[perms[p][1]], dC = ext[perms[p][2]];
         const int G = (dC + LC - 1) / LC;
         if (G > maxG) continue;    // v2: lane g of a warp computes the window of column group g

@@ -186,6 +186,26 @@ def box_filter_periodic(a, sh, sv):
     return out / (sh * sh * sv)
 
 
+def gpu_optimize_model(model, method="LBFGS", iterations=1000, loc=None, steps=10, verbose=True, rank=None, x0=None):
+    """Session form of mpi_optimize (src/mpi_optimize.jl:76-143): there the trainable variables of a TensorFlow graph
+    are flattened into one vector, optimised through the closure form, assigned back, and their values returned by
+    rank 0 (`nothing` on the other ranks).  Here the graph is a model object (`VelocityModel` / `DeviceVelocityModel`:
+    `.loss(x)`, `.grad(x)`, and for the device model `.x0()` / `.n_vars`): returns on rank 0 the list of variable
+    arrays -- [var_change (m, n, l)] and, for the joint driver with free scales, [var_change, scales] -- else None."""
+    rank = _rank() if rank is None else int(rank)
+    if x0 is None:
+        x0 = model.x0() if hasattr(model, "x0") else np.zeros(model.vel0.size)
+    x, hist = gpu_optimize(model.loss, model.grad, np.asarray(x0, dtype=np.float64).ravel(), method=method, iterations=iterations,
+                           loc=loc, steps=steps, verbose=verbose, rank=rank)
+    if rank != 0:
+        return None
+    N = model.vel0.size
+    out = [np.array(x[:N]).reshape(model.vel0.shape)]
+    if x.size > N:
+        out.append(np.array(x[N:]))
+    return out
+
+
 class VelocityModel:
     """x -> fvar = 2*sigmoid(x) - 1 + vel0 -> slowness 1/fvar (inversion.jl:42-43,61) and the L1
     box-filter regulariser lambda * sum|fvar - smooth(fvar)| (:107-121).  `problems`: this rank's

@@ -132,6 +132,21 @@ def test_lbfgs_driver_on_quadratic(lib, tmp_path, capsys):
     assert capsys.readouterr().out == "" and not os.path.exists(tmp_path / "r1")
 
 
+def test_session_form_returns_variable_list(lib, tmp_path):
+    """gpu_optimize_model = the session form of mpi_optimize (:76-143): variables flattened, optimised, returned as a
+    list by rank 0 and as None by the others."""
+    class Model:            # a quadratic "graph": var_change (2,3,2) and one free scale
+        vel0 = np.ones((2, 3, 2))
+        c = np.arange(13, dtype=np.float64) / 7.0
+        def x0(self): return np.zeros(13)
+        def loss(self, z): return float(((np.asarray(z).ravel() - self.c) ** 2).sum())
+        def grad(self, z): return 2.0 * (np.asarray(z).ravel() - self.c)
+    out = lib.gpu_optimize_model(Model(), iterations=50, verbose=False, rank=0)
+    assert [o.shape for o in out] == [(2, 3, 2), (1,)]
+    assert np.abs(np.concatenate([o.ravel() for o in out]) - Model.c).max() < 1e-8
+    assert lib.gpu_optimize_model(Model(), iterations=5, verbose=False, rank=1) is None
+
+
 def test_hdf5_min_roundtrip_and_real_file(lib, tmp_path):
     """The checkpoint writer produces what its reader -- checked here against a file written by libhdf5 itself --
     reads back bit for bit; the datatype message equals the library's byte for byte."""
