@@ -78,6 +78,7 @@ struct adtomo_ctx {
     int force_v0 = 0;                           // debugging aid: ADTOMO_FORCE_V0=1 selects the row-major kernel
     int force_v1 = 0;                           // debugging aid: ADTOMO_FORCE_V1=1 selects the level-major kernel
     int force_v2 = 0;                           // debugging aid: ADTOMO_FORCE_V2=1 selects the skewed-pencil kernel for any batch
+    bool oom = false;                           // a workspace allocation failed since the flag was last cleared
     std::map<std::pair<long long, int>, int> chunk_cache;   // sources per chunk of the fused step, per (grid, batch)
     int v2_pairing = 1;                         // tuning aid: ADTOMO_V2_PAIRING=0 keeps sources in caller order
     std::map<std::tuple<const void *, int, long long>, int *> v2_spent;   // rounds per source of earlier calls, per batch (plan, S, batch id)
@@ -120,6 +121,8 @@ struct Plan2Cache {
     size_t smem_bytes;
     // batch kernel (kernels_fwd_v3.cuh): compile-time row pitch of the instantiation (0: run-time pitch), slot table
     int pct = 0, tabOffset = 0, maxPer = 0;
+    size_t smemNS = 0;          // the plain (not cp.async staged) sweep: plane + slot table only
+    int tabOffsetNS = 0;
     bool v3 = false;
 };
 
@@ -164,7 +167,16 @@ static int ws_get(adtomo_ctx *c, const char *name, size_t bytes, void **out) {
         if (e != cudaSuccess) {
             cudaGetLastError();
             want = bytes;
-            CK(cudaMalloc(&slot.first, want));
+            e = cudaMalloc(&slot.first, want);
+            if (e != cudaSuccess) {
+                // less free memory than when the chunk size of the fused step was derived: forget the cached sizes, the
+                // caller's retry (adtomo_eikonal3d_misfit_grad does one itself) re-derives them from cudaMemGetInfo
+                cudaGetLastError();
+                slot.first = nullptr;
+                c->chunk_cache.clear();
+                c->oom = true;
+                return fail(ADTOMO_ERR_CUDA, "out of device memory: workspace '%s' needs %zu bytes", name, want);
+            }
         }
         slot.second = want;
     }
@@ -525,9 +537,12 @@ static Plan2Cache *get_plan2(adtomo_ctx *c, int m, int n, int l) {
     pc->smem_bytes = pc->ok ? sizeof(double) * (size_t)pc->plan.WCH * pc->plan.PS : 0;
     if (pc->v3) {
         pc->maxPer = v3_max_per_warp(pc->plan);
+        const size_t tabBytes = (sizeof(V3Slot) + sizeof(int)) * (size_t)(pc->plan.NT / 32) * pc->maxPer;
+        pc->tabOffsetNS = (int)((pc->smem_bytes + 15) & ~(size_t)15);      // plain sweep: plane, then the slot table
+        pc->smemNS = pc->tabOffsetNS + tabBytes;
         if (pc->pct) pc->smem_bytes = std::max(pc->smem_bytes, (size_t)V3_STAGE_BYTES_PER_WARP * (pc->plan.NT / 32));   // cp.async staging aliases the plane
         pc->tabOffset = (int)((pc->smem_bytes + 15) & ~(size_t)15);
-        pc->smem_bytes = pc->tabOffset + (sizeof(V3Slot) + sizeof(int)) * (size_t)(pc->plan.NT / 32) * pc->maxPer;
+        pc->smem_bytes = pc->tabOffset + tabBytes;
         if (pc->smem_bytes > (size_t)100 * 1024 || pc->plan.NT > 512) {   // table too large for two CTAs per SM, or more than 16 warps: the round-1 sweep loop
             pc->v3 = false;
             pc->ok = v2_build_plan(pc->plan, m, n, l, vw ? atoi(vw) : 16, 64 * 1024);
@@ -617,13 +632,15 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
 #define V3_LAUNCH(PCT_, STG_)                                                                                          \
     do {                                                                                                               \
         auto kern = ragged ? k_fwd3d_v3<512, 2, PCT_, STG_, true> : k_fwd3d_v3<512, 2, PCT_, STG_, false>;             \
+        const size_t smem__ = STG_ ? pc->smem_bytes : pc->smemNS;                                                      \
+        const int tabOff__ = STG_ ? pc->tabOffset : pc->tabOffsetNS;                                                   \
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                       \
         if (v3_carveout >= 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, v3_carveout)); \
         int occ = 1;                                                                                                   \
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, pc->smem_bytes));                           \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, P.NT, smem__));                                   \
         if (occ < 1) occ = 1;                                                                                          \
         if (c->v2_occ > 0 && occ > c->v2_occ) occ = c->v2_occ;                                                         \
-        kern<<<std::min(S, c->num_sms * occ), P.NT, pc->smem_bytes, c->stream>>>(P, pc->tabOffset, pc->maxPer, bufs, flay, flay + P.M, h, \
+        kern<<<std::min(S, c->num_sms * occ), P.NT, smem__, c->stream>>>(P, tabOff__, pc->maxPer, bufs, flay, flay + P.M, h, \
                                                                                  tol, max_rounds, S, d_rounds, d_errs, where, order, spent); \
     } while (0)
     // cp.async look-ahead through shared memory pays when a CTA has its SM to itself (148 sources: 100 vs 111 ms) and
@@ -1474,8 +1491,15 @@ extern "C" int adtomo_eikonal3d_misfit_grad(adtomo_ctx *c, double *misfit, doubl
                                             const double *qua, int *rounds, int loc) {
     if (!c) return fail(ADTOMO_ERR_ARG, "null context");
     std::lock_guard<std::mutex> lk(c->mu);
-    return misfit_grad_core(c, misfit, grad_f, loc, f, loc, h, m, n, l, tol, max_rounds, S, src_ptr, src_idx, src_val, u0_fill,
-                            E, rcv_xyz, uobs, qua, rounds, loc);
+    c->oom = false;
+    int rc = misfit_grad_core(c, misfit, grad_f, loc, f, loc, h, m, n, l, tol, max_rounds, S, src_ptr, src_idx, src_val, u0_fill,
+                              E, rcv_xyz, uobs, qua, rounds, loc);
+    if (rc == ADTOMO_ERR_CUDA && c->oom) {      // free memory shrank since the chunk size was cached: once more with fresh sizes
+        c->oom = false;
+        rc = misfit_grad_core(c, misfit, grad_f, loc, f, loc, h, m, n, l, tol, max_rounds, S, src_ptr, src_idx, src_val, u0_fill,
+                              E, rcv_xyz, uobs, qua, rounds, loc);
+    }
+    return rc;
 }
 #include "model_api.inc"
 
