@@ -47,7 +47,7 @@
 // everything back from L2 / DRAM: 1.9 us per level at 256^3, 53 % of the warp time in the level barrier).
 #pragma once
 #include <cstring>
-#include "kernels_fwd_v2.cuh"
+#include "kernels_fwd_v3.cuh"
 
 namespace adtomo {
 
@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_team(const Plan2 P, const
     unsigned long long *errslot = (unsigned long long *)(sy + 2);
     tm_u64 *mbox = mbox_all + (long long)src * T.nC * 2 * T.mbStride;
     unsigned epoch = 0, serial = serial0, step = 0;
+    const V3Pol pol = v3_policies();
     double *B3 = bufs + (long long)src * 3 * P.M;
     double *Bz = B3 + 2 * P.M;
     const int A0 = t * T.R, A1 = A0 + T.R < P.dA ? A0 + T.R : P.dA;   // the slabs this CTA owns (and re-skews)
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) k_fwd3d_team(const Plan2 P, const
                 const int next = P.sg[sw + 1][1] * P.sg[sw + 1][2];
                 if (next != state) {                  // the next sweep runs on the other layout: re-skew my slabs
                     double *dst = state > 0 ? Bz : Ba;
-                    v2_reskew(P, w, dst, state, plane, A0, A1);
+                    v3_reskew<0>(P, w, dst, state, plane, A0, A1, pol);      // run-time pitch; thread-owned columns (kernels_fwd_v3.cuh)
                     w = dst;
                     state = next;
                 }
