@@ -707,7 +707,9 @@ static Plan2Cache *get_plan_team(adtomo_ctx *c, int m, int n, int l) {
 }
 
 // KS: slots per warp whose per-sweep constants stay in registers
-static const void *team_kernel(int KS) {
+// one: the launch has at most one CTA per SM -- the instantiation without the 64-register cap (no spills)
+static const void *team_kernel(int KS, bool one = false) {
+    if (one) return KS <= 1 ? (const void *)k_fwd3d_team<512, 1, 1> : (const void *)k_fwd3d_team<512, 1, 2>;
     return KS <= 1 ? (const void *)k_fwd3d_team<512, 2, 1> : (const void *)k_fwd3d_team<512, 2, 2>;
 }
 static size_t team_smem(const Plan2Cache *pc, const TeamCfg &T) {
@@ -779,8 +781,10 @@ static int fwd3d_team(adtomo_ctx *c, const Plan2Cache *pc, const TeamCfg &T, dou
         TeamCfg Tv = T;
         const double *fPp = flay, *fMp = flay + P.M;
         void *args[] = {&Pv, &Tv, &bufs, &fPp, &fMp, &h, &tol, &max_rounds, &d_rounds, &d_errs, &where, &sync, &mbox, &serial0};
-        CK(cudaLaunchCooperativeKernel(team_kernel(team_ks(T, c->team_nt)), dim3(S * T.nC), dim3(c->team_nt), args,
-                                       team_smem(pc, T), c->stream));
+        const bool one = S * T.nC <= c->num_sms && !getenv("ADTOMO_TEAM_CAP64");     // (testing aid: keep the capped kernel)
+        const void *kern = team_kernel(team_ks(T, c->team_nt), one);
+        if (one) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaLaunchCooperativeKernel(kern, dim3(S * T.nC), dim3(c->team_nt), args, team_smem(pc, T), c->stream));
     }
     phase_end(c, pk);
     LAUNCHED(c, "k_fwd3d_team");
