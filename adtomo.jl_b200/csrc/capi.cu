@@ -83,6 +83,7 @@ struct adtomo_ctx {
     int v2_pairing = 1;                         // tuning aid: ADTOMO_V2_PAIRING=0 keeps sources in caller order
     std::map<std::tuple<const void *, int, long long>, int *> v2_spent;   // rounds per source of earlier calls, per batch (plan, S, batch id)
     long long batch_id = 0;                     // adtomo_set_batch_id: names the source batch of the following calls
+    int batch_chunk = 0;                        // chunk of that batch the fused step is working on (every chunk has its own placement memo)
     const char *last_fwd_kernel = "";           // name of the last 3D forward sweep kernel launched (adtomo_last_forward_kernel)
     int v3_mode = 1;                            // ADTOMO_V3: 1 (default) batch sweeps of kernels_fwd_v3.cuh with menu pitch, 2 same with run-time pitch, 0 the round-1 sweep loop (cross-check)
     int v4_mode = 0;                            // ADTOMO_V4: 1 the slot-block sweep of kernels_fwd_v4.cuh where the grid allows it (bit-exact, measured slower: 2.4x the DRAM reads), 0 (default) never
@@ -579,7 +580,7 @@ static int fwd3d_v2(adtomo_ctx *c, const Plan2Cache *pc, double *dU, const doubl
     order = where + S;
     // rounds each source of THIS batch needed last time (batch = plan, size, caller's rounds array)
     {
-        const auto key = std::make_tuple((const void *)pc, S, c->batch_id);
+        const auto key = std::make_tuple((const void *)pc, S, c->batch_id * 4096 + c->batch_chunk);
         auto it = c->v2_spent.find(key);
         if (it == c->v2_spent.end()) {
             if (c->v2_spent.size() > 64) {          // bounded: forget everything
@@ -1442,7 +1443,10 @@ static int misfit_grad_core(adtomo_ctx *c, double *misfit, double *grad_f, int l
         k_scatter_sources<<<(sc + 127) / 128, 128, 0, c->stream>>>(dU0, dptr + s0, didx, dval, d.N, sc);
         LAUNCHED(c, "k_scatter_sources");
         const SparseU0 sp = {dptr + s0, didx, dval, u0_fill, dU0};
-        if ((rc = fwd3d_device(c, dU, df, d, h, tol, max_rounds, sc, dR + s0, nullptr, &sp))) return rc;
+        c->batch_chunk = s0 / Sc;                 // the rounds / placement memo of the batch kernel is per chunk
+        rc = fwd3d_device(c, dU, df, d, h, tol, max_rounds, sc, dR + s0, nullptr, &sp);
+        c->batch_chunk = 0;
+        if (rc) return rc;
         if (grad_f) CK(cudaMemsetAsync(dG, 0, sizeof(double) * cnt, c->stream));
         dim3 g((E + 127) / 128, sc);
         int pkm = phase_begin(c, PH_MISFIT);

@@ -98,3 +98,32 @@ def test_device_model_argument_errors(lib, ctx):
         ctx.model_finish(1e-3, 4, 3, True, None)                   # even window
     loss, rc = ctx.model_finish(0.0, 3, 3, False, None)
     assert loss == 0.0 and rc == 0
+
+
+def test_device_tables_are_validated(lib, ctx):
+    """Index / coordinate tables that live on the device are checked there (the host cannot see them): an index outside the
+    grid or a receiver outside it is an argument error, not an out-of-bounds store."""
+    import torch
+    m, n, l, S, E = 8, 8, 8, 2, 3
+    dev = torch.device("cuda", 0)
+    N = m * n * l
+    f = torch.ones(N, dtype=torch.float64, device=dev)
+    ptr = torch.tensor([0, 1, 2], dtype=torch.int32, device=dev)
+    val = torch.zeros(2, dtype=torch.float64, device=dev)
+    rcv = torch.tensor([[1.0, 2.0, 3.0], [4.5, 4.5, 4.5], [7.0, 7.0, 7.0]], dtype=torch.float64, device=dev)
+    obs = torch.ones(S * E, dtype=torch.float64, device=dev)
+    qua = torch.ones(S * E, dtype=torch.float64, device=dev)
+    packed = torch.zeros(N + 1, dtype=torch.float64, device=dev)
+    good = torch.tensor([10, 100], dtype=torch.int32, device=dev)
+    mis, rc = ctx.misfit_grad(packed, f, 1.0, (m, n, l), 1e-6, S, ptr, good, val, 1000.0, E, rcv, obs, qua, loc=lib.DEVICE)
+    assert rc == 0 and np.isfinite(mis)
+    bad_idx = torch.tensor([10, N + 5], dtype=torch.int32, device=dev)
+    with pytest.raises(lib.AdtomoError, match="src_idx"):
+        ctx.misfit_grad(packed, f, 1.0, (m, n, l), 1e-6, S, ptr, bad_idx, val, 1000.0, E, rcv, obs, qua, loc=lib.DEVICE)
+    bad_rcv = rcv.clone()
+    bad_rcv[1, 2] = 7.5
+    with pytest.raises(lib.AdtomoError, match="receiver"):
+        ctx.misfit_grad(packed, f, 1.0, (m, n, l), 1e-6, S, ptr, good, val, 1000.0, E, bad_rcv, obs, qua, loc=lib.DEVICE)
+    # the context is still usable
+    mis2, rc = ctx.misfit_grad(packed, f, 1.0, (m, n, l), 1e-6, S, ptr, good, val, 1000.0, E, rcv, obs, qua, loc=lib.DEVICE)
+    assert rc == 0 and abs(mis2 - mis) <= 1e-12 * abs(mis)
