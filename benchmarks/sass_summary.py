@@ -14,13 +14,18 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "adtomo.jl_b200", "libadtomo_b200.so")
 KERNELS = {   # mangled-name fragments -> label
-    "k_fwd3d_v3ILi512ELi2ELi72ELb0": "k_fwd3d_v3<512,2,72,false> (bench C3 forward)",
-    "k_fwd3d_v3ILi512ELi2ELi104ELb0": "k_fwd3d_v3<512,2,104,false> (bench C4 forward)",
+    "k_fwd3d_v3ILi512ELi2ELi72ELb0ELb0": "k_fwd3d_v3<512,2,72,false,false> (bench C3 forward: plain sweep, no ragged edge)",
+    "k_fwd3d_v3ILi512ELi2ELi104ELb0ELb0": "k_fwd3d_v3<512,2,104,false,false> (bench C4 forward)",
+    "k_fwd3d_v3ILi512ELi2ELi72ELb0ELb1": "k_fwd3d_v3<512,2,72,false,true> (ragged grids: lane mask)",
+    "k_fwd3d_v3ILi512ELi2ELi72ELb1ELb0": "k_fwd3d_v3<512,2,72,true,false> (cp.async staged sweep: one CTA per SM)",
+    "k_fwd3d_v4ILi512ELi2ELi72": "k_fwd3d_v4<512,2,72> (opt-in slot-block sweep)",
     "k_adj3d_sparseILi1024": "k_adj3d_sparse<1024> (bench adjoint)",
     "k_adj3d_topo2ILi1024ELb1": "k_adj3d_topo2<1024,true> (dense-rhs adjoint)",
     "k_adj3d_setup3": "k_adj3d_setup3",
     "k_fwd3d_teamILi512ELi2ELi1": "k_fwd3d_team<512,2,1>",
     "k_fwd3d_teamILi512ELi2ELi2": "k_fwd3d_team<512,2,2>",
+    "k_fwd3d_teamILi512ELi1ELi1": "k_fwd3d_team<512,1,1> (at most one CTA per SM: no register cap)",
+    "k_fwd3d_teamILi512ELi1ELi2": "k_fwd3d_team<512,1,2>",
     "k_adj3d_topo_teamILi512ELi4096": "k_adj3d_topo_team<512>",
     "k_model_fwd": "k_model_fwd (on-device parametrisation)",
 }
