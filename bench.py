@@ -433,6 +433,7 @@ def run_ours(args):
               "scaling": "strong", "value": C4_SOURCES * args.c4_steps / (R4["ms_dev"] * 1e-3), "unit": UNIT,
               "ms_per_step": R4["ms_dev"] / args.c4_steps, "steps": args.c4_steps, "warmup": 2, "sources_per_gpu": R4["S"],
               "forward_ms": float(R4["phases"][0]), "adjoint_ms": float(R4["phases"][3]), "rounds_mean": float(r4.mean()),
+              "rounds_hist": {str(int(k)): int(v) for k, v in zip(*np.unique(r4, return_counts=True))},
               "misfit": R4["mis_dev"][0]}
 
     # ---- BASELINE configs[1] (C2, one 64^3 source) and configs[4] (C5, one 256^3 / 512^3 source): single-source solves on
